@@ -1,0 +1,668 @@
+// alr_kernels.cuh — device descriptors and kernels of the renderer (sm_100a).
+//
+// Pipeline per chunk of events (each kernel cites the reference code it replaces):
+//   k_ir_fft      RIR partitions -> packed half spectra (+ per-partition energy)      synthesize.py:103,298,425
+//   k_ir_scale    per-IR normalisation scalar a_l                                      synthesize.py:404-428,560
+//   k_x_fft       source blocks x cross-fade weight g_l -> spectra                     synthesize.py:148-181,299
+//   k_cmac        Y[b,c] = sum_{l,j,k: xb0_l+j+k=b} X_l[j] * H_l[k,c]                  synthesize.py:184-252 / :103
+//   k_ifft_ola    inverse FFT + overlap-add + truncation + max|y|, sum|y| partials     synthesize.py:255-274,590
+//   k_event_gain  apply_snr / db_to_multiplier scalars                                 synthesize.py:40-68,594-599
+//   k_apply_gain  y *= gain                                                            synthesize.py:594,599
+//   k_amb_*       mean|ambience| -> scale                                              synthesize.py:350-352
+//   k_mix         scene = sum ambience*scale + sum events in [start,end)               synthesize.py:328-378
+#pragma once
+#include "alr_fft.cuh"
+
+namespace alr {
+
+constexpr int kCtaThreads = kGroup * kGroupsPerCta;  // 256
+constexpr int kChanGroup = 4;                        // channels per CMAC / IFFT CTA
+constexpr int kRun = 4;                              // consecutive output blocks per IFFT CTA (tail kept in registers)
+constexpr int kBinCtas = kP / (2 * kCtaThreads);     // CMAC CTAs per spectrum (each thread: 2 bins = one float4)
+
+enum { kGainEvent = 0, kGainNone = 1, kGainDry = 2, kGainPass = 3 };  // Pass: already rendered, only mixed
+
+struct EvDev {
+  const float* x;    // dry audio (Lx)
+  const float* irs;  // RIR taps
+  float* y;          // out (C, n_out)
+  long long ir_stride_c, ir_stride_n;
+  long long hslot0, xslot0, yslot0;  // first spectrum slot of this event in the chunk workspace
+  int Lx, Lh, C, N, K;
+  int n_out;    // samples per channel in y
+  int n_valid;  // samples that carry signal; [n_valid, n_out) is zero filled
+  int B_valid;  // ceil(n_valid / P): blocks with spectra
+  int B_out;    // ceil(n_out / P)
+  int xlimit;   // source samples >= xlimit are not needed / zero
+  int ir0;      // first IrDev of this event
+  int blk0;     // first entry of the per-output-block IR range table
+  int moving, normalize, gain_mode;
+  int mask_lo, mask_hi;  // taps outside [mask_lo, mask_hi) are treated as zero (dry / direct-path window)
+  int parent;            // dry events: stats index of the parent event, else -1
+  int stat;              // index into the stats array
+  int part0, nparts;     // range of reduction partials written by k_ifft_ola
+  int dry_channel, dry_low, dry_high;
+  double snr, ref_db;
+};
+
+struct IrDev {
+  int xb0;    // first source block in which IR l is active
+  int xnb;    // number of active source blocks
+  int xslot;  // event-local index of the first X spectrum of this IR (prefix sum of xnb)
+  int woff;   // offset of this IR's cross-fade weight band
+  int jmin;   // first STFT frame (row of the interpolation matrix) of the band
+  int nrows;  // band length
+};
+
+struct EvStat {
+  double peak, mean_abs, gain, event_scale, a0;
+  int nonfinite, dry_peak;
+};
+
+struct SceneDev {
+  float* mix;
+  int C;
+  int n_amb;
+  long long T;
+  int amb0;  // first AmbDev
+  int ev0;   // first entry in the scene's event list
+  int nev;
+};
+
+struct AmbDev {
+  const float* data;
+  long long n;  // C*T
+  double ref_db;
+  float scale;
+  int part0, nparts;
+};
+
+struct MixEv {
+  const float* y;
+  long long start, end;
+  int n_out;
+  int pad;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_segment(const int* __restrict__ prefix, int n, int idx) {
+  // largest e in [0, n) with prefix[e] <= idx   (prefix has n + 1 entries, prefix[0] = 0)
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(prefix + mid) <= idx) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_ir_fft: one 64-thread group per RIR partition (event e, IR l, partition k, capsule c).
+// Spectrum slot = hslot0 + (l*K + k)*C + c, i.e. layout [l][k][c][P] so that k_cmac reads the C capsules of one
+// (l,k) contiguously.  Also writes the partition's energy sum(h^2) for normalize_irs.
+__global__ void __launch_bounds__(kCtaThreads)
+k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, int n_tasks,
+         const float2* __restrict__ tw, float2* __restrict__ hspec, float* __restrict__ hen) {
+  __shared__ FftSmem sm[kGroupsPerCta];
+  __shared__ float s_red[kGroupsPerCta][2];
+  const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
+  const int task = blockIdx.x * kGroupsPerCta + g;
+  if (task >= n_tasks) return;  // whole group leaves together
+  const int e = find_segment(prefix, n_ev, task);
+  const EvDev& ev = evs[e];
+  int local = task - __ldg(prefix + e);
+  const int c = local % ev.C;
+  local /= ev.C;
+  const int k = local % ev.K;
+  const int l = local / ev.K;
+  const float* src = ev.irs + (long long)c * ev.ir_stride_c + (long long)l * ev.ir_stride_n;
+  const int t0 = k * kP;
+  const int lo = max(ev.mask_lo, t0), hi = min(min(ev.mask_hi, ev.Lh), t0 + kP);
+  float2 v[16];
+  float en = 0.f;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(src + t0) & 7u) == 0);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int n = t0 + 2 * (t + 64 * r);
+    float a = 0.f, b = 0.f;
+    if (vec_ok && n >= lo && n + 1 < hi) {
+      float2 p = __ldg(reinterpret_cast<const float2*>(src + n));
+      a = p.x;
+      b = p.y;
+    } else {
+      if (n >= lo && n < hi) a = __ldg(src + n);
+      if (n + 1 >= lo && n + 1 < hi) b = __ldg(src + n + 1);
+    }
+    v[r] = make_float2(a, b);
+    en = fmaf(a, a, en);
+    en = fmaf(b, b, en);
+  }
+#pragma unroll
+  for (int r = 8; r < 16; ++r) v[r] = make_float2(0.f, 0.f);
+  const long long slot = ev.hslot0 + (long long)(l * ev.K + k) * ev.C + c;
+  en = warp_sum(en);
+  if ((t & 31) == 0) s_red[g][t >> 5] = en;
+  rfft_block_to_global(v, sm[g], tw, t, bar, hspec + slot * kP);  // contains group barriers
+  if (t == 0) hen[slot] = s_red[g][0] + s_red[g][1];
+}
+
+// k_ir_scale: a_l = 1 / mean_c( sqrt(sum_t h_{l,c}^2) + tiny )  (normalize_irs on the (N, C, Lh) view), times 512
+// for moving events (the un-normalised irfft of istft_overlap_synthesis, synthesize.py:267). One warp per IR.
+__global__ void k_ir_scale(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ ir_prefix, int n_irs,
+                           const float* __restrict__ hen, float* __restrict__ irscale, EvStat* __restrict__ stats) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_irs) return;
+  const int e = find_segment(ir_prefix, n_ev, w);
+  const EvDev& ev = evs[e];
+  const int l = w - __ldg(ir_prefix + e);
+  double a = 1.0;
+  if (ev.gain_mode == kGainDry) {
+    a = stats[ev.parent].a0;  // the parent's a_0: compute_dry_audio gets the normalised IRs (synthesize.py:608)
+  } else if (ev.normalize) {
+    double mean_e = 0.0;
+    for (int c = 0; c < ev.C; ++c) {
+      float s = 0.f;
+      for (int k = lane; k < ev.K; k += 32) s += hen[ev.hslot0 + (long long)(l * ev.K + k) * ev.C + c];
+      s = warp_sum(s);
+      mean_e += sqrt((double)s) + 2.2250738585072014e-308;
+    }
+    mean_e /= ev.C;
+    a = mean_e > 0.0 ? 1.0 / mean_e : 0.0;
+    if (!(a < 3.0e38)) a = 0.0;  // all-zero IR: the reference yields exact zeros (0 / tiny)
+  }
+  if (lane == 0) {
+    if (l == 0 && ev.gain_mode != kGainDry) stats[ev.stat].a0 = a;
+    irscale[ev.ir0 + l] = (float)(ev.moving ? 512.0 * a : a);
+  }
+}
+
+// k_x_fft: one group per (event, IR l, active source block j). Input sample t = (xb0+j)*P + n is
+// x[t] * irscale_l * g_l(t), with g_l(t) = w[q,l] cos^2(pi p/256) + w[q+1,l] sin^2(pi p/256), q = t / 128,
+// p = t % 128: the Hann-smoothed source-side cross-fade that is equivalent to the reference's STFT-domain
+// interpolation (generate_interpolation_matrix + stft window, synthesize.py:120,148-181).
+__global__ void __launch_bounds__(kCtaThreads)
+k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, int n_tasks,
+        const IrDev* __restrict__ irs, const float* __restrict__ wband, const float* __restrict__ irscale,
+        const float2* __restrict__ tw, const float* __restrict__ win, float2* __restrict__ xspec) {
+  __shared__ FftSmem sm[kGroupsPerCta];
+  const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
+  const int task = blockIdx.x * kGroupsPerCta + g;
+  if (task >= n_tasks) return;
+  const int e = find_segment(prefix, n_ev, task);
+  const EvDev& ev = evs[e];
+  const int local = task - __ldg(prefix + e);
+  // IR owning this X slot: largest l with xslot[l] <= local
+  int l = 0;
+  {
+    int lo = 0, hi = ev.N;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (irs[ev.ir0 + mid].xslot <= local) lo = mid; else hi = mid;
+    }
+    l = lo;
+  }
+  const IrDev ir = irs[ev.ir0 + l];
+  const int j = local - ir.xslot;
+  const int t0 = (ir.xb0 + j) * kP;
+  const float sc = irscale[ev.ir0 + l];
+  const float* __restrict__ x = ev.x;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(x + t0) & 7u) == 0);
+  float s0 = 0.f, s1 = 0.f;
+  if (ev.moving) {
+    s0 = __ldg(win + 2 * t);
+    s1 = __ldg(win + 2 * t + 1);
+  }
+  float2 v[16];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int n = t0 + 2 * (t + 64 * r);
+    float a = 0.f, b = 0.f;
+    if (vec_ok && n + 1 < ev.xlimit) {
+      float2 p = __ldg(reinterpret_cast<const float2*>(x + n));
+      a = p.x;
+      b = p.y;
+    } else {
+      if (n < ev.xlimit) a = __ldg(x + n);
+      if (n + 1 < ev.xlimit) b = __ldg(x + n + 1);
+    }
+    float ga = sc, gb = sc;
+    if (ev.moving) {
+      const int q = (n >> 7) - ir.jmin;  // frame q and q+1 cover samples n, n+1 (n even, n % 128 <= 126)
+      const float w0 = (q >= 0 && q < ir.nrows) ? __ldg(wband + ir.woff + q) : 0.f;
+      const float w1 = (q + 1 >= 0 && q + 1 < ir.nrows) ? __ldg(wband + ir.woff + q + 1) : 0.f;
+      ga = sc * fmaf(w1 - w0, s0, w0);  // w0 (1 - s) + w1 s
+      gb = sc * fmaf(w1 - w0, s1, w0);
+    }
+    v[r] = make_float2(a * ga, b * gb);
+  }
+#pragma unroll
+  for (int r = 8; r < 16; ++r) v[r] = make_float2(0.f, 0.f);
+  rfft_block_to_global(v, sm[g], tw, t, bar, xspec + (ev.xslot0 + local) * kP);
+}
+
+// k_cmac: one CTA per (event, output block b, group of 4 capsules, half of the bins); a thread owns 2 bins.
+// Y[b,c] = sum over IRs l active for b, source blocks j of l with k = b - xb0_l - j in [0, K):  X_l[j] * H_l[k,c].
+// RIR-partition spectra are read as coalesced float4 (2 bins) loads straight from L2.
+__global__ void __launch_bounds__(kCtaThreads)
+k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const IrDev* __restrict__ irs,
+       const int2* __restrict__ lrange, const float4* __restrict__ xspec, const float4* __restrict__ hspec,
+       float4* __restrict__ yspec) {
+  const int e = find_segment(prefix, n_ev, blockIdx.x);
+  const EvDev& ev = evs[e];
+  int local = blockIdx.x - __ldg(prefix + e);
+  const int br = local % kBinCtas;
+  local /= kBinCtas;
+  const int ncg = (ev.C + kChanGroup - 1) / kChanGroup;
+  const int cg = local % ncg;
+  const int b = local / ncg;
+  const int c0 = cg * kChanGroup;
+  const int nc = min(kChanGroup, ev.C - c0);
+  const int i = br * kCtaThreads + threadIdx.x;  // float4 index inside a spectrum (bins 2i, 2i+1)
+  const bool is_dc = (i == 0);
+  float4 acc[kChanGroup];
+  float2 dc[kChanGroup];
+#pragma unroll
+  for (int c = 0; c < kChanGroup; ++c) {
+    acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dc[c] = make_float2(0.f, 0.f);
+  }
+  const int2 lr = lrange[ev.blk0 + b];
+  constexpr int S = kP / 2;  // float4 per spectrum
+  for (int l = lr.x; l <= lr.y; ++l) {
+    const IrDev ir = irs[ev.ir0 + l];
+    const int d = b - ir.xb0;
+    const int j_lo = max(0, d - ev.K + 1), j_hi = min(ir.xnb - 1, d);
+    const float4* xp = xspec + (ev.xslot0 + ir.xslot) * S + i;
+    const float4* hp = hspec + (ev.hslot0 + (long long)l * ev.K * ev.C + c0) * S + i;
+#pragma unroll 2
+    for (int j = j_lo; j <= j_hi; ++j) {
+      const int k = d - j;
+      const float4 xv = __ldg(xp + (long long)j * S);
+      const float4* hk = hp + (long long)k * ev.C * S;
+#pragma unroll
+      for (int c = 0; c < kChanGroup; ++c) {
+        if (c < nc) {
+          const float4 hv = __ldg(hk + (long long)c * S);
+          acc[c].x = fmaf(xv.x, hv.x, acc[c].x);
+          acc[c].x = fmaf(-xv.y, hv.y, acc[c].x);
+          acc[c].y = fmaf(xv.x, hv.y, acc[c].y);
+          acc[c].y = fmaf(xv.y, hv.x, acc[c].y);
+          acc[c].z = fmaf(xv.z, hv.z, acc[c].z);
+          acc[c].z = fmaf(-xv.w, hv.w, acc[c].z);
+          acc[c].w = fmaf(xv.z, hv.w, acc[c].w);
+          acc[c].w = fmaf(xv.w, hv.z, acc[c].w);
+          if (is_dc) {  // packed bin 0 = (DC, Nyquist): two real products
+            dc[c].x = fmaf(xv.x, hv.x, dc[c].x);
+            dc[c].y = fmaf(xv.y, hv.y, dc[c].y);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kChanGroup; ++c) {
+    if (c < nc) {
+      if (is_dc) {
+        acc[c].x = dc[c].x;
+        acc[c].y = dc[c].y;
+      }
+      yspec[(ev.yslot0 + (long long)b * ev.C + c0 + c) * S + i] = acc[c];
+    }
+  }
+}
+
+// k_ifft_ola: one CTA per (event, group of 4 capsules, run of kRun output blocks); group g handles capsule c0+g.
+// Inverse FFT of Y[b], overlap-add with the tail of block b-1 (kept in registers: the thread that produces
+// tail samples of block b is the one that needs them for block b+1), scale 1/(2P), truncate to n_valid, zero
+// fill up to n_out (pad_or_truncate_audio, utils.py:667), and reduce max|y| and sum|y| per CTA.
+__global__ void __launch_bounds__(kCtaThreads)
+k_ifft_ola(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const float2* __restrict__ tw,
+           const float2* __restrict__ yspec, float2* __restrict__ partials, int part_base) {
+  __shared__ FftSmem sm[kGroupsPerCta];
+  __shared__ float s_max[kCtaThreads / 32], s_sum[kCtaThreads / 32];
+  const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
+  const int e = find_segment(prefix, n_ev, blockIdx.x);
+  const EvDev& ev = evs[e];
+  int local = blockIdx.x - __ldg(prefix + e);
+  const int nruns = (ev.B_out + kRun - 1) / kRun;
+  const int run = local % nruns;
+  const int cg = local / nruns;
+  const int c = cg * kChanGroup + g;
+  float vmax = 0.f, vsum = 0.f;
+  if (c < ev.C) {
+    const float inv = 1.0f / (2.0f * kP);
+    float* __restrict__ y = ev.y + (long long)c * ev.n_out;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(y) & 7u) == 0);
+    float2 tail[4][2];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) tail[m][0] = tail[m][1] = make_float2(0.f, 0.f);
+    const int b0 = run * kRun;
+    const int b1 = min(b0 + kRun, ev.B_out);
+    for (int b = b0 - 1; b < b1; ++b) {
+      if (b < 0) continue;
+      float2 o[4][4];
+      if (b < ev.B_valid) {
+        irfft_block_from_global(yspec + (ev.yslot0 + (long long)b * ev.C + c) * kP, sm[g], tw, t, bar, o);
+      } else {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[m][k] = make_float2(0.f, 0.f);
+      }
+      if (b >= b0) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int n = b * kP + 2 * (t + 64 * m + 256 * k);  // output sample index (even)
+            float a = (o[m][k].x + tail[m][k].x) * inv;
+            float bb = (o[m][k].y + tail[m][k].y) * inv;
+            if (n >= ev.n_valid) a = 0.f;
+            if (n + 1 >= ev.n_valid) bb = 0.f;
+            if (vec_ok && n + 1 < ev.n_out) {
+              *reinterpret_cast<float2*>(y + n) = make_float2(a, bb);
+            } else {
+              if (n < ev.n_out) y[n] = a;
+              if (n + 1 < ev.n_out) y[n + 1] = bb;
+            }
+            vmax = fmaxf(vmax, fmaxf(fabsf(a), fabsf(bb)));
+            vsum += fabsf(a) + fabsf(bb);
+          }
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        tail[m][0] = o[m][2];
+        tail[m][1] = o[m][3];
+      }
+    }
+  }
+  vmax = warp_max(vmax);
+  vsum = warp_sum(vsum);
+  if ((threadIdx.x & 31) == 0) {
+    s_max[threadIdx.x >> 5] = vmax;
+    s_sum[threadIdx.x >> 5] = vsum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f, s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCtaThreads / 32; ++w) {
+      m = fmaxf(m, s_max[w]);
+      s += s_sum[w];
+    }
+    partials[part_base + blockIdx.x] = make_float2(m, s);
+  }
+}
+
+// k_tile: events without IRs — dry audio repeated on every capsule (synthesize.py:572-577). One CTA per
+// (event, slice); partial reductions like k_ifft_ola.
+__global__ void k_tile(const EvDev* __restrict__ evs, const int* __restrict__ list, int slices,
+                       float2* __restrict__ partials) {
+  __shared__ float s_max[32], s_sum[32];
+  const EvDev& ev = evs[list[blockIdx.y]];
+  float vmax = 0.f, vsum = 0.f;
+  const long long total = (long long)ev.C * ev.n_out;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % ev.n_out);
+    const float a = n < ev.Lx ? ev.x[n] : 0.f;
+    ev.y[i] = a;
+    vmax = fmaxf(vmax, fabsf(a));
+    vsum += fabsf(a);
+  }
+  vmax = warp_max(vmax);
+  vsum = warp_sum(vsum);
+  if ((threadIdx.x & 31) == 0) {
+    s_max[threadIdx.x >> 5] = vmax;
+    s_sum[threadIdx.x >> 5] = vsum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f, s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      m = fmaxf(m, s_max[w]);
+      s += s_sum[w];
+    }
+    partials[ev.part0 + blockIdx.x] = make_float2(m, s);
+  }
+  (void)slices;
+}
+
+// k_event_gain: one warp per event. Follows apply_snr + db_to_multiplier literally, in double:
+//   M = max(1e-15, max|y|); y1 = y * snr / M; m = mean|y1|; S = 10^((ref_db+snr)/20) / (m + tiny); out = S * y1.
+__global__ void k_event_gain(const EvDev* __restrict__ evs, int ev_begin, int ev_end,
+                             const float2* __restrict__ partials, EvStat* __restrict__ stats,
+                             float* __restrict__ gains) {
+  const int w = ev_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= ev_end) return;
+  const EvDev& ev = evs[w];
+  if (ev.gain_mode == kGainPass) return;
+  float m = 0.f;
+  double s = 0.0;
+  for (int p = lane; p < ev.nparts; p += 32) {
+    float2 v = partials[ev.part0 + p];
+    m = fmaxf(m, v.x);
+    s += (double)v.y;
+  }
+  m = warp_max(m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane != 0) return;
+  EvStat& st = stats[ev.stat];
+  const double count = (double)ev.C * (double)ev.n_out;
+  const double mean_abs = s / count;
+  const int bad = !(isfinite(s) && isfinite((double)m));
+  double gain = 1.0, scale = 1.0;
+  const double peak = fmax(1e-15, (double)m);
+  if (ev.gain_mode == kGainEvent) {
+    const double m1 = fabs(ev.snr) * mean_abs / peak;  // mean|y * snr / M|
+    scale = pow(10.0, (ev.ref_db + ev.snr) / 20.0) / (m1 + 2.2250738585072014e-308);
+    gain = (m > 0.f) ? scale * ev.snr / peak : 0.0;    // y == 0 stays 0 (the reference multiplies 0 first)
+  } else if (ev.gain_mode == kGainDry) {
+    gain = stats[ev.parent].event_scale;                // dry * event_scale (synthesize.py:493)
+    scale = gain;
+  }
+  if (ev.gain_mode == kGainDry) {
+    st.nonfinite |= bad;
+  } else {
+    st.peak = peak;
+    st.mean_abs = mean_abs;
+    st.gain = gain;
+    st.event_scale = scale;
+    st.nonfinite = bad;
+  }
+  gains[w] = (float)gain;
+}
+
+// k_apply_gain: y *= gain for every event of the chunk. grid = (slices, events)
+__global__ void k_apply_gain(const EvDev* __restrict__ evs, int ev_begin, const float* __restrict__ gains) {
+  const EvDev& ev = evs[ev_begin + blockIdx.y];
+  if (ev.gain_mode == kGainNone || ev.gain_mode == kGainPass) return;
+  const float gain = gains[ev_begin + blockIdx.y];
+  const long long total = (long long)ev.C * ev.n_out;
+  float* __restrict__ y = ev.y;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(y) & 15u) == 0) {
+    float4* y4 = reinterpret_cast<float4*>(y);
+    const long long n4 = total >> 2;
+    for (long long q = i; q < n4; q += stride) {
+      float4 v = y4[q];
+      v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain;
+      y4[q] = v;
+    }
+    for (long long q = (n4 << 2) + i; q < total; q += stride) y[q] *= gain;
+  } else {
+    for (; i < total; i += stride) y[i] *= gain;
+  }
+}
+
+// k_dry_window: peak = argmax(irs[ref, 0, :]) (signed, first occurrence; synthesize.py:482) and the tap window
+// [peak - low, peak + high) that compute_dry_audio keeps (:484-487). One CTA per dry event; writes the mask into
+// the event descriptor that k_ir_fft reads afterwards.
+__global__ void k_dry_window(EvDev* __restrict__ evs, const int* __restrict__ list, EvStat* __restrict__ stats) {
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  EvDev& ev = evs[list[blockIdx.x]];
+  const float* h = ev.irs;  // already offset to (ref channel, IR 0)
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int n = threadIdx.x; n < ev.Lh; n += blockDim.x) {
+    float v = h[n];
+    if (v > best) { best = v; bi = n; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) { best = s_v[w]; bi = s_i[w]; }
+    if (bi == 0x7fffffff) bi = 0;  // all-NaN row: numpy's argmax would return the first NaN; flagged via nonfinite
+    // ir[peak+high:] = 0 if peak+high < Lh ; ir[:peak-low] = 0 if peak-low > 0
+    ev.mask_hi = (bi + ev.dry_high < ev.Lh) ? bi + ev.dry_high : ev.Lh;
+    ev.mask_lo = (bi - ev.dry_low > 0) ? bi - ev.dry_low : 0;
+    stats[ev.parent].dry_peak = bi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ambience: sum|a| partials -> scale = 10^(ref_db/20) / (mean|a| + tiny)      (synthesize.py:350-352)
+__global__ void k_amb_partial(const AmbDev* __restrict__ ambs, float* __restrict__ partials) {
+  __shared__ float s_sum[32];
+  const AmbDev& a = ambs[blockIdx.y];
+  float s = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(a.data) & 15u) == 0) {
+    const float4* d4 = reinterpret_cast<const float4*>(a.data);
+    const long long n4 = a.n >> 2;
+    for (long long q = i; q < n4; q += stride) {
+      float4 v = __ldg(d4 + q);
+      s += (fabsf(v.x) + fabsf(v.y)) + (fabsf(v.z) + fabsf(v.w));
+    }
+    for (long long q = (n4 << 2) + i; q < a.n; q += stride) s += fabsf(a.data[q]);
+  } else {
+    for (; i < a.n; i += stride) s += fabsf(a.data[i]);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_sum[w];
+    partials[a.part0 + blockIdx.x] = tot;
+  }
+}
+
+__global__ void k_amb_final(AmbDev* __restrict__ ambs, int n_amb, const float* __restrict__ partials) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_amb) return;
+  AmbDev& a = ambs[w];
+  double s = 0.0;
+  for (int p = lane; p < a.nparts; p += 32) s += (double)partials[a.part0 + p];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const double mean = s / (double)a.n;
+    const double sc = pow(10.0, a.ref_db / 20.0) / (mean + 2.2250738585072014e-308);
+    a.scale = mean > 0.0 ? (float)sc : 0.f;  // all-zero ambience contributes zeros in the reference too
+  }
+}
+
+// k_mix: scene[c, t] = sum_a scale_a * amb_a[c, t] + sum_e y_e[c, t - start_e] for start_e <= t < end_e, added in
+// the reference's order (ambience first, then events in dict order) with one float32 rounding per term like
+// the reference's float32 scene buffer (synthesize.py:332,356,378). grid = (time tiles, scenes); every thread
+// owns 4 samples strided by the CTA width so all accesses are coalesced whatever the event offsets are.
+__global__ void __launch_bounds__(256)
+k_mix(const SceneDev* __restrict__ scenes, const AmbDev* __restrict__ ambs, const MixEv* __restrict__ mevs) {
+  const SceneDev& sc = scenes[blockIdx.y];
+  const long long tile0 = (long long)blockIdx.x * 1024;
+  if (tile0 >= sc.T) return;
+  const long long tile1 = min(tile0 + 1024, sc.T);
+  for (int c = 0; c < sc.C; ++c) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int a = 0; a < sc.n_amb; ++a) {
+      const AmbDev& am = ambs[sc.amb0 + a];
+      const float* __restrict__ d = am.data + (long long)c * sc.T;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long tt = tile0 + threadIdx.x + 256 * q;
+        if (tt < tile1) acc[q] = fmaf(am.scale, __ldg(d + tt), acc[q]);
+      }
+    }
+    for (int k = 0; k < sc.nev; ++k) {
+      const MixEv& me = mevs[sc.ev0 + k];
+      if (me.end <= tile0 || me.start >= tile1) continue;  // uniform per CTA
+      const float* __restrict__ y = me.y + (long long)c * me.n_out;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long tt = tile0 + threadIdx.x + 256 * q;
+        const long long idx = tt - me.start;
+        if (tt < tile1 && tt >= me.start && tt < me.end && idx < me.n_out) acc[q] += __ldg(y + idx);
+      }
+    }
+    float* __restrict__ out = sc.mix + (long long)c * sc.T;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long tt = tile0 + threadIdx.x + 256 * q;
+      if (tt < tile1) out[tt] = acc[q];
+    }
+  }
+}
+
+// ---- unit-test kernels for the FFT core ---------------------------------------------------------------------
+__global__ void __launch_bounds__(kCtaThreads)
+k_debug_rfft(const float* __restrict__ in, long long n_blocks, long long in_stride, int n_valid,
+             const float2* __restrict__ tw, float2* __restrict__ spec) {
+  __shared__ FftSmem sm[kGroupsPerCta];
+  const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
+  const long long blk = (long long)blockIdx.x * kGroupsPerCta + g;
+  if (blk >= n_blocks) return;
+  const float* src = in + blk * in_stride;
+  float2 v[16];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int n = 2 * (t + 64 * r);
+    v[r] = make_float2(n < n_valid ? src[n] : 0.f, n + 1 < n_valid ? src[n + 1] : 0.f);
+  }
+#pragma unroll
+  for (int r = 8; r < 16; ++r) v[r] = make_float2(0.f, 0.f);
+  rfft_block_to_global(v, sm[g], tw, t, bar, spec + blk * kP);
+}
+
+__global__ void __launch_bounds__(kCtaThreads)
+k_debug_irfft(const float2* __restrict__ spec, long long n_blocks, const float2* __restrict__ tw,
+              float* __restrict__ out) {
+  __shared__ FftSmem sm[kGroupsPerCta];
+  const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
+  const long long blk = (long long)blockIdx.x * kGroupsPerCta + g;
+  if (blk >= n_blocks) return;
+  float2 o[4][4];
+  irfft_block_from_global(spec + blk * kP, sm[g], tw, t, bar, o);
+  const float inv = 1.0f / (2.0f * kP);
+  float* dst = out + blk * 2 * kP;
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int n = 2 * (t + 64 * m + 256 * k);
+      dst[n] = o[m][k].x * inv;
+      dst[n + 1] = o[m][k].y * inv;
+    }
+}
+
+}  // namespace alr

@@ -1,0 +1,307 @@
+"""Low-level host API: flat event / scene jobs -> one `alr_render` call of the C-ABI library.
+
+Arrays may be numpy arrays (host path, ALR_MEM_HOST) or CUDA torch tensors (device-resident path,
+ALR_MEM_DEVICE); torch is used only for allocation and `data_ptr()` hand-off.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import ALR_GAIN_EVENT, ALR_GAIN_NONE, ALR_MEM_DEVICE, ALR_MEM_HOST, AlrEvent, AlrEventStats, AlrProfile, AlrScene
+
+FFT_SIZE, WIN_SIZE, HOP_SIZE = 512, 256, 128  # the only STFT geometry the kernels implement (config.py:9-11)
+
+
+# ---- bit-exact host arithmetic shared by every entry point ------------------------------------------------------
+def n_stft_frames(n_samples: int, hop_size: int = HOP_SIZE) -> int:
+    """Number of STFT frames the reference computes for a signal (synthesize.py:123)."""
+    return 2 * int(np.ceil(n_samples / (2.0 * hop_size))) + 1
+
+
+def moving_frames(duration: float, sample_rate: float, n_irs: int, n_audio: int,
+                  hop_size: int = HOP_SIZE) -> Tuple[np.ndarray, int]:
+    """IR start frames and frame count of a moving event, with the reference's own expressions:
+    ir_times = linspace(0, duration, N) (synthesize.py:302); frames = np.round((t*sr + hop)/hop) (:169, half to
+    even); n_frames = min(audio frames, int(frames[-1])) (:170, :208-210)."""
+    ir_times = np.linspace(0, duration, n_irs)
+    frames = np.round((ir_times * sample_rate + hop_size) / hop_size)
+    n_w = int(frames[-1])
+    return frames.astype(np.int32), min(n_stft_frames(n_audio, hop_size), n_w)
+
+
+def event_slice(scene_start: float, scene_end: float, sample_rate, total: int) -> Tuple[int, int]:
+    """Sample slice of an event in the scene buffer (synthesize.py:361-362): Python round(), half to even."""
+    return max(0, round(scene_start * sample_rate)), min(round(scene_end * sample_rate), total)
+
+
+def scene_samples(duration, sample_rate) -> int:
+    """T = round(scene.duration * scene.sample_rate) (synthesize.py:331)."""
+    return round(duration * sample_rate)
+
+
+# ---- jobs ---------------------------------------------------------------------------------------------------------
+@dataclass
+class EventJob:
+    """One (event, microphone) render; mirrors `alr_event` of include/alrender.h."""
+    audio: object = None                  # (Lx,) float32
+    irs: object = None                    # (C, N, Lh) float32 (any strides with a contiguous last axis) or None
+    n_channels: int = 0
+    snr: float = 0.0
+    ref_db: float = -65.0
+    ir_frames: Optional[np.ndarray] = None  # int32 (N,) for moving events
+    n_frames: int = 0
+    normalize_irs: bool = True
+    gain_mode: int = ALR_GAIN_EVENT
+    n_out: Optional[int] = None           # default: len(audio)
+    dry: Optional[Tuple[int, int, int]] = None  # (ref channel, low samples, high samples)
+    scene: int = -1
+    scene_start: int = 0
+    scene_end: int = 0
+    spatial: object = None                # (C, n_out) float32 out (allocated when None); INPUT when prerendered
+    dry_out: object = None                # (Lx+Lh-1,) float32 out
+    prerendered: bool = False             # spatial is an input that is only mixed
+    stats: Optional[dict] = None
+
+
+@dataclass
+class SceneJob:
+    """One (scene, microphone) mixdown; mirrors `alr_scene`."""
+    n_channels: int
+    n_samples: int
+    ambience: Sequence[object] = ()       # each (C, T) float32
+    ambience_ref_db: Sequence[float] = ()
+    mix: object = None                    # (C, T) float32 out
+
+
+def _is_torch(a) -> bool:
+    return hasattr(a, "data_ptr")
+
+
+def _ptr(a) -> int:
+    if a is None:
+        return 0
+    return a.data_ptr() if _is_torch(a) else a.ctypes.data
+
+
+def _strides_elems(a):
+    if _is_torch(a):
+        return tuple(a.stride())
+    return tuple(s // a.itemsize for s in a.strides)
+
+
+class Renderer:
+    """One context per GPU (alr_create). Not thread-safe; calls block until results are ready."""
+
+    def __init__(self, device: int = -1, workspace_limit: Optional[int] = None, profiling: bool = False):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.alr_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = device
+        if workspace_limit is not None:
+            _lib.check(self._lib.alr_set_workspace_limit(self._h, int(workspace_limit)))
+        if profiling:
+            _lib.check(self._lib.alr_set_profiling(self._h, 1))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.alr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_profiling(self, enable: bool):
+        _lib.check(self._lib.alr_set_profiling(self._h, 1 if enable else 0))
+
+    def profile(self) -> dict:
+        p = AlrProfile()
+        _lib.check(self._lib.alr_get_profile(self._h, C.byref(p)))
+        return {k: getattr(p, k) for k, _ in AlrProfile._fields_}
+
+    # -- marshalling ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def _alloc_like(ref, shape):
+        if _is_torch(ref):
+            import torch
+            return torch.empty(shape, dtype=torch.float32, device=ref.device)
+        return np.empty(shape, dtype=np.float32)
+
+    def pack(self, events: Sequence[EventJob], scenes: Sequence[SceneJob]):
+        """Builds the ctypes descriptor arrays once (reusable across repeated render calls on the same buffers)."""
+        keep = []
+        n_ev, n_sc = len(events), len(scenes)
+        ev_arr = (AlrEvent * max(n_ev, 1))()
+        device_mode = None
+        for i, e in enumerate(events):
+            a = ev_arr[i]
+            ref = e.spatial if e.prerendered else e.audio
+            mode = _is_torch(ref)
+            if device_mode is None:
+                device_mode = mode
+            elif device_mode != mode:
+                raise ValueError("cannot mix host (numpy) and device (torch) buffers in one call")
+            C_ = int(e.n_channels)
+            if e.prerendered:
+                n_out = int(e.spatial.shape[1])
+                a.n_irs = -1
+                a.n_channels = C_
+                a.n_out = n_out
+                a.spatial = _ptr(e.spatial)
+                a.gain_mode = ALR_GAIN_NONE
+            else:
+                lx = int(e.audio.shape[0])
+                n_out = int(e.n_out) if e.n_out is not None else lx
+                a.audio = _ptr(e.audio)
+                a.n_audio = lx
+                n_irs = 0 if e.irs is None else int(e.irs.shape[1])
+                a.n_irs = n_irs
+                a.n_channels = C_
+                if n_irs > 0:
+                    sc, sn, st = _strides_elems(e.irs)
+                    if st != 1:
+                        raise ValueError("IR taps must be contiguous along the last axis")
+                    if int(e.irs.shape[0]) != C_:
+                        raise ValueError("irs.shape[0] != n_channels")
+                    a.irs = _ptr(e.irs)
+                    a.ir_stride_c, a.ir_stride_n = int(sc), int(sn)
+                    a.n_ir_samples = int(e.irs.shape[2])
+                if n_irs > 1:
+                    fr = np.ascontiguousarray(e.ir_frames, dtype=np.int32)
+                    if fr.shape != (n_irs,):
+                        raise ValueError("ir_frames must have one entry per IR")
+                    keep.append(fr)
+                    a.ir_frames = fr.ctypes.data
+                    a.n_frames = int(e.n_frames)
+                a.normalize_irs = 1 if e.normalize_irs else 0
+                a.gain_mode = int(e.gain_mode)
+                a.snr = float(e.snr)
+                a.ref_db = float(e.ref_db)
+                if e.spatial is None:
+                    e.spatial = self._alloc_like(e.audio, (C_, n_out))
+                if tuple(e.spatial.shape) != (C_, n_out):
+                    raise ValueError(f"spatial buffer has shape {tuple(e.spatial.shape)}, expected {(C_, n_out)}")
+                a.spatial = _ptr(e.spatial)
+                a.n_out = n_out
+                if e.dry is not None:
+                    ch, lo, hi = e.dry
+                    a.dry_channel, a.dry_low, a.dry_high = int(ch), int(lo), int(hi)
+                    n_dry = lx + int(e.irs.shape[2]) - 1
+                    if e.dry_out is None:
+                        e.dry_out = self._alloc_like(e.audio, (n_dry,))
+                    a.dry = _ptr(e.dry_out)
+            a.scene = int(e.scene)
+            a.scene_start = int(e.scene_start)
+            a.scene_end = int(e.scene_end)
+        sc_arr = (AlrScene * max(n_sc, 1))()
+        for i, s in enumerate(scenes):
+            b = sc_arr[i]
+            b.n_channels = int(s.n_channels)
+            b.n_samples = int(s.n_samples)
+            n_amb = len(s.ambience)
+            b.n_ambience = n_amb
+            if n_amb:
+                for amb in s.ambience:
+                    if tuple(amb.shape) != (s.n_channels, s.n_samples):
+                        raise ValueError(
+                            f"Scene ambient noise does not match expected shape. "
+                            f"Expected {(s.n_channels, s.n_samples)}, but got {tuple(amb.shape)}.")
+                    if device_mode is None:
+                        device_mode = _is_torch(amb)
+                ptrs = (C.c_void_p * n_amb)(*[_ptr(amb) for amb in s.ambience])
+                dbs = (C.c_double * n_amb)(*[float(d) for d in s.ambience_ref_db])
+                keep += [ptrs, dbs]
+                b.ambience = C.cast(ptrs, C.c_void_p)
+                b.ambience_ref_db = C.cast(dbs, C.c_void_p)
+            if s.mix is None:
+                ref = s.ambience[0] if n_amb else next((e.spatial for e in events if e.spatial is not None), None)
+                if ref is None:
+                    ref = np.empty(0, dtype=np.float32)
+                s.mix = self._alloc_like(ref, (s.n_channels, s.n_samples))
+            b.mix = _ptr(s.mix)
+        stats = (AlrEventStats * max(n_ev, 1))()
+        return dict(ev=ev_arr, sc=sc_arr, n_ev=n_ev, n_sc=n_sc, stats=stats, keep=keep,
+                    mode=ALR_MEM_DEVICE if device_mode else ALR_MEM_HOST, events=events, scenes=scenes)
+
+    def run(self, packed, stream: int = 0):
+        """One alr_render call on pre-packed descriptors. `stream` is a raw cudaStream_t (0 = default stream)."""
+        rc = self._lib.alr_render(self._h, packed["ev"], packed["n_ev"], packed["sc"], packed["n_sc"], packed["mode"],
+                                  packed["stats"], C.c_void_p(stream))
+        _lib.check(rc)
+        return packed["stats"]
+
+    def render(self, events: Sequence[EventJob], scenes: Sequence[SceneJob] = (), stream: int = 0):
+        """Renders the events (+ optional scene mixdowns) and fills `spatial` / `dry_out` / `mix` and `stats`."""
+        packed = self.pack(events, scenes)
+        st = self.run(packed, stream)
+        for i, e in enumerate(events):
+            s = st[i]
+            e.stats = dict(peak=s.peak, mean_abs=s.mean_abs, gain=s.gain, event_scale=s.event_scale,
+                           nonfinite=bool(s.nonfinite), dry_peak=s.dry_peak)
+        return events, scenes
+
+    # -- FFT unit-test hooks ----------------------------------------------------------------------------------------
+    def debug_rfft(self, blocks):
+        """blocks: CUDA float32 tensor (n_blocks, n_valid<=P) -> packed spectra (n_blocks, P, 2)."""
+        import torch
+        P = self._lib.alr_partition_size()
+        n_blocks, n_valid = blocks.shape
+        out = torch.empty((n_blocks, P, 2), dtype=torch.float32, device=blocks.device)
+        _lib.check(self._lib.alr_debug_rfft(self._h, blocks.data_ptr(), n_blocks, blocks.stride(0), n_valid,
+                                            out.data_ptr(), None))
+        return out
+
+    def debug_irfft(self, spec):
+        import torch
+        P = self._lib.alr_partition_size()
+        n_blocks = spec.shape[0]
+        out = torch.empty((n_blocks, 2 * P), dtype=torch.float32, device=spec.device)
+        _lib.check(self._lib.alr_debug_irfft(self._h, spec.data_ptr(), n_blocks, out.data_ptr(), None))
+        return out
+
+
+def debug_plan(job: EventJob) -> dict:
+    """Host-only: the partition plan the C++ planner derives for one event (no GPU needed)."""
+    lib = _lib.load()
+    dummy = np.zeros(1, dtype=np.float32)
+    lx = int(job.audio.shape[0])
+    a = AlrEvent()
+    a.audio = _ptr(job.audio)
+    a.n_audio = lx
+    n_irs = int(job.irs.shape[1])
+    a.n_irs = n_irs
+    a.n_channels = int(job.n_channels)
+    sc, sn, _ = _strides_elems(job.irs)
+    a.irs = _ptr(job.irs)
+    a.ir_stride_c, a.ir_stride_n = int(sc), int(sn)
+    a.n_ir_samples = int(job.irs.shape[2])
+    fr = None
+    if n_irs > 1:
+        fr = np.ascontiguousarray(job.ir_frames, dtype=np.int32)
+        a.ir_frames = fr.ctypes.data
+        a.n_frames = int(job.n_frames)
+    a.n_out = int(job.n_out) if job.n_out is not None else lx
+    a.spatial = dummy.ctypes.data
+    a.scene = -1
+    header = np.zeros(8, dtype=np.int32)
+    cap_ir = 6 * max(n_irs, 1)
+    irs = np.zeros(cap_ir, dtype=np.int32)
+    cap_w = 4 * (int(job.n_frames) + 2 * n_irs + 16)
+    wband = np.zeros(cap_w, dtype=np.float32)
+    cap_l = 2 * (a.n_out // 64 + 16)
+    lrange = np.zeros(cap_l, dtype=np.int32)
+    _lib.check(lib.alr_debug_plan(C.byref(a), header.ctypes.data, irs.ctypes.data, cap_ir, wband.ctypes.data, cap_w,
+                                  lrange.ctypes.data, cap_l))
+    K, B_valid, B_out, n_valid, xlimit, n_ir, n_w, n_l = [int(v) for v in header]
+    return dict(K=K, B_valid=B_valid, B_out=B_out, n_valid=n_valid, xlimit=xlimit,
+                irs=irs[:6 * n_ir].reshape(n_ir, 6).copy(), wband=wband[:n_w].copy(),
+                lrange=lrange[:2 * n_l].reshape(n_l, 2).copy(), P=lib.alr_partition_size())

@@ -1,0 +1,182 @@
+/*
+ * alrender.h — C-ABI of the B200-native renderer for AudibleLight's synthesis hot path.
+ *
+ * The reference (AudibleLight v0.1.2, pure Python) has no FFI for this path; its seam is three module-level
+ * functions of audiblelight/synthesize.py that Scene.generate imports at call time (core.py:1828-1838):
+ *
+ *     render_event_audio(event, irs, mic_alias, ref_db, ...)        synthesize.py:507-608
+ *     render_audio_for_all_scene_events(scene, ignore_cache)        synthesize.py:613-677
+ *     generate_scene_audio_from_events(scene)                       synthesize.py:314-401
+ *
+ * The Python host layer (audiblelight_b200/synthesize.py) keeps those names and signatures, does the
+ * validation / exception mapping / bit-exact timing arithmetic, and hands flat descriptors to the entry
+ * points below through ctypes.  Everything here is plain pointers and sizes; no torch
+ * or C++ types cross the boundary.  All functions return ALR_OK (0) or a negative status;
+ * alr_last_error() gives the message of the last failure on the calling thread.
+ *
+ * One context per GPU.  A context owns only its workspace (twiddle tables, spectra, descriptors, staging);
+ * every input and output buffer belongs to the caller.
+ */
+#ifndef ALRENDER_H
+#define ALRENDER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALR_VERSION 100
+
+enum {
+  ALR_OK = 0,
+  ALR_ERR_INVALID = -1,   /* bad argument / descriptor */
+  ALR_ERR_CUDA = -2,      /* CUDA runtime failure (message has the CUDA error string) */
+  ALR_ERR_NOMEM = -3,
+  ALR_ERR_NO_DEVICE = -4  /* no usable CUDA device: there is NO CPU fallback */
+};
+
+/* where the caller's buffers live */
+enum { ALR_MEM_HOST = 0, ALR_MEM_DEVICE = 1 };
+
+/* what happens to the convolved signal y of an event after the convolution */
+enum {
+  /* reference render_event_audio: y * snr / max|y| then * 10^((ref_db+snr)/20) / (mean|.| + tiny)
+     (apply_snr synthesize.py:40-49 + db_to_multiplier :52-68, used at :594-599) */
+  ALR_GAIN_EVENT = 0,
+  /* raw convolution output, as time_invariant_convolution (:71-106) / time_variant_convolution (:277-310) */
+  ALR_GAIN_NONE = 1
+};
+
+typedef struct alr_context alr_context;
+
+/*
+ * One (event, microphone) render = one call of the reference's render_event_audio (synthesize.py:507).
+ * All sample data is float32 (the reference computes in float64; the contract is max-abs error <= 1e-5 of
+ * full scale, BASELINE.json north_star).
+ */
+typedef struct alr_event {
+  /* ---- inputs ---- */
+  const float* audio;       /* (n_audio) mono dry audio == Event.load_audio() (event.py:496-539) */
+  int64_t n_audio;          /* Lx */
+  const float* irs;         /* RIR taps; element (capsule c, emitter l, tap t) at irs[c*ir_stride_c + l*ir_stride_n + t]
+                               (the reference layout is (C, N, Lh), worldstate.py:2183-2255) */
+  int64_t ir_stride_c;      /* in elements */
+  int64_t ir_stride_n;      /* in elements */
+  int32_t n_channels;       /* C: capsules of the microphone (micarrays.py n_capsules) */
+  int32_t n_irs;            /* N: 0 = no IR, dry audio tiled over C channels (:572-577); 1 = static (:564-569);
+                               >1 = moving, time-variant convolution (:580-587);
+                               -1 = already rendered: `spatial` is an INPUT (C, n_out) that is only mixed into its
+                               scene (generate_scene_audio_from_events called on cached event.spatial_audio) */
+  int64_t n_ir_samples;     /* Lh */
+  const int32_t* ir_frames; /* HOST pointer, (n_irs): STFT frame at which each IR starts, i.e.
+                               int(np.round((ir_times*sr + 128)/128)) of synthesize.py:169; NULL unless n_irs > 1 */
+  int32_t n_frames;         /* moving only: min(n_audio_frames, n_weight_frames) of synthesize.py:208-210 */
+  int32_t normalize_irs;    /* 1: apply normalize_irs (synthesize.py:404-428 as called at :560); 0: use taps as given */
+  int32_t gain_mode;        /* ALR_GAIN_EVENT or ALR_GAIN_NONE */
+  double snr;               /* event.snr */
+  double ref_db;            /* scene.ref_db */
+  /* ---- dry / direct-path audio, compute_dry_audio (synthesize.py:432-504); dry == NULL disables it ---- */
+  int32_t dry_channel;      /* event.ref_ir_channel */
+  int32_t dry_low;          /* int(low_ms * sr / 1000) */
+  int32_t dry_high;         /* int(high_ms * sr / 1000) */
+  int32_t reserved0;
+  float* dry;               /* out (n_audio + n_ir_samples - 1) -> event._spatial_audio_dry[mic] */
+  /* ---- output ---- */
+  float* spatial;           /* out (n_channels, n_out) row-major -> event.spatial_audio[mic] */
+  int64_t n_out;            /* samples per channel to produce: n_audio for render_event_audio (pad_or_truncate,
+                               :590); n_audio+n_ir_samples-1 for the raw static convolution */
+  /* ---- placement in a scene mix (generate_scene_audio_from_events, synthesize.py:359-378) ---- */
+  int32_t scene;            /* index into the scenes array of the same call, or -1: do not mix */
+  int32_t reserved1;
+  int64_t scene_start;      /* max(0, round(event.scene_start*sr))                 (:361) */
+  int64_t scene_end;        /* min(round(event.scene_end*sr), n_samples); events with end<=start are skipped (:362-369) */
+} alr_event;
+
+/* One (scene, microphone) mixdown = one iteration of the mic loop of generate_scene_audio_from_events (:325-401). */
+typedef struct alr_scene {
+  int32_t n_channels;            /* C */
+  int32_t n_ambience;            /* number of ambience layers (scene.ambience, :335-356) */
+  int64_t n_samples;             /* T = round(scene.duration * sr) (:331) */
+  const float* const* ambience;  /* HOST array of n_ambience pointers, each (C, T) float32 == Ambience.load_ambience() */
+  const double* ambience_ref_db; /* HOST array (n_ambience) */
+  float* mix;                    /* out (C, T) float32 -> scene.audio[mic] */
+} alr_scene;
+
+/* Per-event numbers the host layer needs back (always HOST memory). */
+typedef struct alr_event_stats {
+  double peak;        /* max|y| over the (C, n_out) block before gain  (apply_snr's denominator, clamp 1e-15 applied) */
+  double mean_abs;    /* mean|y| over the same block */
+  double gain;        /* total multiplier applied to y */
+  double event_scale; /* db_to_multiplier(ref_db+snr, mean|apply_snr(y)|) == `event_scale` of synthesize.py:598 */
+  int32_t nonfinite;  /* 1 if y held NaN/Inf (librosa.util.valid_audio would raise, :603) */
+  int32_t dry_peak;   /* argmax used by compute_dry_audio (:482), -1 if no dry audio */
+} alr_event_stats;
+
+/* Timing / accounting of the last alr_render call (device times from CUDA events on the render stream). */
+typedef struct alr_profile {
+  double ms_total;          /* whole call on the device, incl. copies in ALR_MEM_HOST mode */
+  double ms_ir_fft;         /* RIR partition spectra kernel */
+  double ms_x_fft;          /* cross-fade + source block spectra kernel */
+  double ms_cmac;           /* spectral multiply-accumulate kernel */
+  double ms_ifft;           /* inverse FFT + overlap-add + reductions kernel */
+  double ms_mix;            /* gain + mixdown kernels (incl. ambience reduction) */
+  double ms_other;
+  int64_t kernel_launches;  /* kernels launched by the call */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int64_t workspace_bytes;
+  int64_t n_chunks;
+} alr_profile;
+
+int alr_version(void);
+const char* alr_last_error(void);
+/* sizeof() of the ABI structs as compiled: 0 alr_event, 1 alr_scene, 2 alr_event_stats, 3 alr_profile
+ * (lets a binding verify its mirror of the layout; returns -1 for an unknown id) */
+int alr_struct_size(int which);
+
+/* device < 0: current device. Fails with ALR_ERR_NO_DEVICE when there is no GPU. */
+int alr_create(int device, alr_context** out);
+void alr_destroy(alr_context* ctx);
+
+/* Upper bound for the spectra workspace (bytes); work is cut into chunks that fit. Default 2 GiB. */
+int alr_set_workspace_limit(alr_context* ctx, int64_t bytes);
+/* 1: record per-kernel CUDA-event timings into alr_profile (adds event records, no syncs). Default 0. */
+int alr_set_profiling(alr_context* ctx, int enable);
+
+/*
+ * Render n_events events and mix n_scenes scenes.
+ *   mem_space   ALR_MEM_DEVICE: audio / irs / ambience / spatial / dry / mix are device pointers on ctx's GPU;
+ *               ALR_MEM_HOST:   they are host pointers; the call stages them through pinned memory, copies
+ *                               inputs host->device and results device->host on `stream`.
+ *   stats       HOST array (n_events) or NULL.
+ *   stream      a cudaStream_t (as void*), NULL = the legacy default stream.
+ * The call returns after the work has been enqueued AND completed (it synchronises `stream`): results and
+ * stats are valid on return.
+ */
+int alr_render(alr_context* ctx, const alr_event* events, int64_t n_events, const alr_scene* scenes,
+               int64_t n_scenes, int mem_space, alr_event_stats* stats, void* stream);
+
+int alr_get_profile(alr_context* ctx, alr_profile* out);
+
+/* ---- unit-test hooks for the FFT core (device pointers) -------------------------------------------------
+ * Forward: n_blocks real blocks of `n_valid` (<= partition) samples each, zero-padded to 2*partition ->
+ * packed half spectra (partition complex values per block; bin 0 holds (Re X[0], Re X[partition])).
+ * Inverse: packed spectra -> 2*partition real samples per block, scaled by 1/(2*partition). */
+int alr_partition_size(void);
+int alr_debug_rfft(alr_context* ctx, const float* in, int64_t n_blocks, int64_t in_stride, int32_t n_valid,
+                   float* spec_out, void* stream);
+int alr_debug_irfft(alr_context* ctx, const float* spec_in, int64_t n_blocks, float* out, void* stream);
+
+/* Host-only (no GPU needed): runs the planner on ONE event and returns its partition plan.
+ *   header[8] = {K, B_valid, B_out, n_valid, xlimit, n_irs, n_wband, n_lrange}
+ *   irs       n_irs x 6 int32: {xb0, xnb, xslot, woff, jmin, nrows} per IR
+ *   wband     cross-fade weight bands (float32), lrange: {lmin, lmax} per output block.
+ * Buffers that are too small (capacity in elements) make the call fail with ALR_ERR_INVALID. */
+int alr_debug_plan(const alr_event* ev, int32_t* header, int32_t* irs, int64_t irs_cap, float* wband,
+                   int64_t wband_cap, int32_t* lrange, int64_t lrange_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALRENDER_H */

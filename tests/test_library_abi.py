@@ -1,0 +1,44 @@
+"""CPU: the C-ABI library loads and exports every symbol include/alrender.h declares; no compute without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "audiblelight_b200", "libalrender.so")
+pytestmark = pytest.mark.skipif(not os.path.exists(LIB), reason="libalrender.so not built")
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "alrender.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(alr_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    from audiblelight_b200 import _lib
+    names = _declared()
+    assert "alr_render" in names and "alr_create" in names
+    lib = C.CDLL(LIB)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in alrender.h but not exported"
+    assert sorted(s[0] for s in _lib.SYMBOLS) == names
+
+
+def test_struct_sizes_match_header():
+    from audiblelight_b200 import _lib
+    lib = _lib.load()  # load() itself raises on a mismatch
+    for which, mirror in enumerate((_lib.AlrEvent, _lib.AlrScene, _lib.AlrEventStats, _lib.AlrProfile)):
+        assert lib.alr_struct_size(which) == C.sizeof(mirror)
+    assert lib.alr_struct_size(99) == -1
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from audiblelight_b200 import _lib
+    from audiblelight_b200.renderer import Renderer
+    with pytest.raises(_lib.AlrenderError, match="no CUDA device|no CPU fallback"):
+        Renderer(0)
