@@ -516,7 +516,7 @@ void alr_destroy(alr_context* ctx) {
 }
 
 int alr_set_workspace_limit(alr_context* ctx, int64_t bytes) {
-  if (!ctx || bytes < (1 << 20)) return fail(ALR_ERR_INVALID, "alr_set_workspace_limit: bad argument");
+  if (!ctx || bytes < (1 << 16)) return fail(ALR_ERR_INVALID, "alr_set_workspace_limit: bad argument");
   ctx->ws_limit = bytes;
   return ALR_OK;
 }

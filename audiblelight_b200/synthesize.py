@@ -1,1 +1,407 @@
-"""placeholder — replaced below"""
+"""Drop-in replacements for the synthesis hot path of `audiblelight/synthesize.py` (reference lines cited per
+function). Same names, signatures, side effects and error strings; the arithmetic runs in the CUDA library.
+
+    import audiblelight_b200.synthesize as syn
+    syn.install()           # rebinds the three functions Scene.generate imports at call time (core.py:1828-1838)
+    scene.generate(...)     # now renders on the GPU
+
+or call `render_event_audio`, `render_audio_for_all_scene_events`, `generate_scene_audio_from_events`,
+`time_invariant_convolution`, `time_variant_convolution` directly, or `render_scenes([...])` for whole batches.
+
+The objects passed in are the reference's own `Scene` / `Event` / `Ambience` (duck-typed here: nothing from the
+reference package is imported unless `install()` is called). There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import threading
+from collections import OrderedDict
+from time import time
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+try:  # same logger as the reference when available
+    from loguru import logger
+except Exception:  # pragma: no cover
+    import logging
+
+    logger = logging.getLogger("audiblelight_b200")
+
+from .renderer import (ALR_GAIN_EVENT, ALR_GAIN_NONE, FFT_SIZE, HOP_SIZE, WIN_SIZE, EventJob, Renderer, SceneJob,
+                       event_slice, moving_frames, scene_samples)
+
+DEFAULT_REF_DB = -65  # config.py:23
+
+try:  # the reference raises librosa's ParameterError from librosa.util.valid_audio (synthesize.py:552,603,398)
+    from librosa.util.exceptions import ParameterError  # type: ignore
+except Exception:
+    class ParameterError(ValueError):
+        """Stand-in for librosa.util.exceptions.ParameterError when librosa is not installed."""
+
+
+_renderers = {}
+_lock = threading.Lock()
+
+
+def get_renderer(device: int = -1) -> Renderer:
+    """Per-process, per-device renderer context (alr_create is done once)."""
+    with _lock:
+        r = _renderers.get(device)
+        if r is None:
+            r = Renderer(device)
+            _renderers[device] = r
+        return r
+
+
+# ---- small host helpers (utils.py / validation), exact reference semantics ---------------------------------------
+def _valid_audio(y: np.ndarray) -> None:
+    """librosa.util.valid_audio as the path uses it: floating dtype and finite everywhere."""
+    y = np.asarray(y)
+    if not np.issubdtype(y.dtype, np.floating):
+        raise ParameterError("Audio data must be floating-point")
+    if not np.isfinite(y).all():
+        raise ParameterError("Audio buffer is not finite everywhere")
+
+
+def _validate_shape(shape_a, shape_b) -> None:
+    """utils.validate_shape (utils.py:483-503)."""
+    n = max(len(shape_a), len(shape_b))
+    pa = tuple(shape_a) + (None,) * (n - len(shape_a))
+    pb = tuple(shape_b) + (None,) * (n - len(shape_b))
+    for i, (a, b) in enumerate(zip(pa, pb)):
+        if a is not None and b is not None and a != b:
+            raise ValueError(f"Incompatible shapes at index {i}: {a} != {b} (full shapes: {pa} vs {pb})")
+
+
+def _check_stft_geometry(fft_size, win_size, hop_size) -> None:
+    """The kernels are specialised for the geometry the reference always uses (render_audio_for_all_scene_events
+    never passes anything else, synthesize.py:666-672)."""
+    for name, v in (("fft_size", fft_size), ("win_size", win_size), ("hop_size", hop_size)):
+        if isinstance(v, bool) or not isinstance(v, (int, float, np.integer, np.floating)):
+            raise TypeError("Expected a positive numeric input, but got {}".format(type(v)))
+        if v < 0:
+            raise ValueError(f"Expected a positive numeric input, but got {v}")
+    if (int(fft_size), int(win_size), int(hop_size)) != (FFT_SIZE, WIN_SIZE, HOP_SIZE):
+        raise ValueError(
+            f"audiblelight_b200 implements fft_size/win_size/hop_size = {FFT_SIZE}/{WIN_SIZE}/{HOP_SIZE} only, "
+            f"got {fft_size}/{win_size}/{hop_size}")
+
+
+def _as_f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ---- raw convolutions ------------------------------------------------------------------------------------------------
+def time_invariant_convolution(audio: np.ndarray, ir: np.ndarray) -> np.ndarray:
+    """synthesize.py:71-106 — mono audio (n_samples,) * IR (n_ir_samples, n_channels) -> (n_channels, n+m-1)."""
+    if audio.ndim != 1:
+        raise ValueError(f"Only mono input is supported, but got {audio.ndim} dimensions!")
+    if ir.ndim != 2:
+        raise ValueError(
+            f"Expected shape of IR should be (n_samples, n_channels), but got ({ir.shape}) instead"
+        )
+    lh, n_ch = ir.shape
+    irs = _as_f32(np.asarray(ir).T)[:, None, :]
+    job = EventJob(audio=_as_f32(audio), irs=irs, n_channels=n_ch, normalize_irs=False, gain_mode=ALR_GAIN_NONE,
+                   n_out=audio.shape[0] + lh - 1)
+    get_renderer().render([job])
+    return job.spatial.astype(np.float64)
+
+
+def time_variant_convolution(irs: np.ndarray, event, fft_size=FFT_SIZE, win_size=WIN_SIZE, hop_size=HOP_SIZE) -> np.ndarray:
+    """synthesize.py:277-310 — irs (n_channels, n_irs, n_ir_samples), audio from event.load_audio() ->
+    (n_channels, n_frames*hop - win)."""
+    _check_stft_geometry(fft_size, win_size, hop_size)
+    audio = event.load_audio()
+    n_ch, n_irs, _ = irs.shape
+    frames, n_frames = moving_frames(event.duration, event.sample_rate, len(event), audio.shape[0])
+    if len(event) != n_irs:
+        raise ValueError(f"Event has {len(event)} emitters but {n_irs} IRs were given")
+    n_out = max(n_frames * HOP_SIZE - WIN_SIZE, 0)
+    if n_out == 0:
+        return np.zeros((n_ch, 0))
+    job = EventJob(audio=_as_f32(audio), irs=_as_f32(irs), n_channels=n_ch, ir_frames=frames, n_frames=n_frames,
+                   normalize_irs=False, gain_mode=ALR_GAIN_NONE, n_out=n_out)
+    get_renderer().render([job])
+    return job.spatial.astype(np.float64)
+
+
+# ---- event rendering ----------------------------------------------------------------------------------------------------
+def _event_job(event, irs: np.ndarray, ref_db, ignore_cache: bool) -> EventJob:
+    """Everything render_event_audio does on the host before the arithmetic (synthesize.py:544-587)."""
+    n_ch, n_emitters, n_ir_samples = irs.shape
+    audio = event.load_audio(ignore_cache=ignore_cache, normalize=True)
+    _valid_audio(audio)
+    n_audio = audio.shape[0]
+    job = EventJob(audio=_as_f32(audio), n_channels=n_ch, snr=float(event.snr), ref_db=float(ref_db), n_out=n_audio)
+    if n_emitters == 1:
+        if event.is_moving:
+            raise ValueError("Moving Event has only one emitter!")
+        job.irs = _as_f32(irs)
+    elif n_emitters == 0:
+        logger.warning(
+            f"No IRs were found for Event with alias {event.alias}. Audio is being tiled along the "
+            f"channel dimension to match the expected shape {n_ch, n_audio}."
+        )
+        job.irs = None
+    else:
+        if not event.is_moving:
+            raise ValueError("Expected a moving event!")
+        if len(event) != n_emitters:
+            raise ValueError(f"Event has {len(event)} emitters but {n_emitters} IRs were given")
+        job.irs = _as_f32(irs)
+        job.ir_frames, job.n_frames = moving_frames(event.duration, event.sample_rate, len(event), n_audio)
+    # dry / direct-path audio (compute_dry_audio, synthesize.py:432-504)
+    ref_ch = getattr(event, "ref_ir_channel", None)
+    dp = getattr(event, "direct_path_time_ms", None)
+    if ref_ch is not None and dp is not None:
+        if ref_ch > n_ch:  # sic (synthesize.py:470)
+            raise ValueError(f"Reference channel index out of range for IRs with {n_ch} channels")
+        if n_emitters > 0:
+            if ref_ch >= n_ch:
+                raise IndexError(f"index {ref_ch} is out of bounds for axis 0 with size {n_ch}")
+            low, high = dp
+            job.dry = (int(ref_ch), int(low * event.sample_rate / 1000), int(high * event.sample_rate / 1000))
+    elif ref_ch is not None or dp is not None:
+        logger.warning(
+            "Only one of `ref_ir_channel` or `direct_path_time` were specified when creating the Event. "
+            "Dry audio will not be computed for this Event. Pass both variables to compute dry audio."
+        )
+    return job
+
+
+def _store_event_result(event, job: EventJob, mic_alias: str) -> None:
+    n_ch, n_audio = job.n_channels, job.audio.shape[0]
+    if job.stats["nonfinite"]:
+        raise ParameterError("Audio buffer is not finite everywhere")
+    spatial = job.spatial.astype(np.float64) if job.irs is not None else job.spatial  # N == 0 stays float32 (:577)
+    _validate_shape(spatial.shape, (n_ch, n_audio))
+    event.spatial_audio[mic_alias] = spatial
+    if job.dry is not None:
+        event._spatial_audio_dry[mic_alias] = job.dry_out.astype(np.float64)
+
+
+def render_event_audio(event, irs: np.ndarray, mic_alias: str, ref_db=DEFAULT_REF_DB, ignore_cache: Optional[bool] = True,
+                       fft_size=FFT_SIZE, win_size=WIN_SIZE, hop_size=HOP_SIZE) -> None:
+    """synthesize.py:507-608 — renders `event.spatial_audio[mic_alias]` (and the dry audio when requested)."""
+    if mic_alias in event.spatial_audio.keys() and not ignore_cache:
+        return
+    _check_stft_geometry(fft_size, win_size, hop_size)
+    job = _event_job(event, np.asarray(irs), ref_db, ignore_cache)
+    get_renderer().render([job])
+    _store_event_result(event, job, mic_alias)
+
+
+def validate_scene(scene) -> None:
+    """synthesize.py:681-739 — same checks, same messages."""
+    if scene.state.num_emitters == 0:
+        raise ValueError("WorldState has no emitters!")
+    if len(scene.state.microphones) == 0:
+        raise ValueError("WorldState has no microphones!")
+    if len(scene.events) == 0:
+        raise ValueError("Scene has no events!")
+    total_ems = 0
+    for alias, ev in scene.events.items():
+        try:
+            total_ems += len(ev)
+        except ValueError:
+            raise ValueError(f"Event with alias '{alias}' has no emitters registered. Has it been orphaned?")
+    if not scene.state.name.upper() == "RLR":
+        return
+    if scene.state.ctx.get_listener_count() == 0:
+        raise ValueError("Ray-tracing engine has no listeners!")
+    if scene.state.ctx.get_source_count() == 0:
+        raise ValueError("Ray-tracing engine has no sources!")
+    vals = (total_ems, scene.state.num_emitters, scene.state.ctx.get_source_count())
+    if not all(v == vals[0] for v in vals):
+        raise ValueError(
+            f"Mismatching number of emitters, events, and sources! "
+            f"Got {len(scene.events)} events, {scene.state.num_emitters} emitters, "
+            f"{scene.state.ctx.get_source_count()} sources. "
+            f"Have any been orphaned?"
+        )
+    capsules = sum(m.n_listeners for m in scene.state.microphones.values())
+    if capsules != scene.state.ctx.get_listener_count():
+        raise ValueError(
+            f"Mismatching number of microphones and listeners! "
+            f"Got {capsules} capsules, {scene.state.ctx.get_listener_count()} listeners. "
+            f"Have any been orphaned?"
+        )
+
+
+def _scene_event_jobs(scene, ignore_cache: bool):
+    """(mic, event) jobs of one scene in the reference's loop order (synthesize.py:653-675), honouring the cache."""
+    if ignore_cache:
+        scene.state.simulate()
+    else:
+        try:
+            _ = scene.state.irs
+        except AttributeError:
+            scene.state.simulate()
+    validate_scene(scene)
+    irs = scene.state.get_irs()
+    jobs = []
+    for mic_alias, mic_ir in irs.items():
+        emitter_counter = 0
+        for _, event in scene.events.items():
+            n = len(event)
+            event_irs = mic_ir[:, emitter_counter:n + emitter_counter, :]
+            if not (mic_alias in event.spatial_audio.keys() and not ignore_cache):
+                jobs.append((mic_alias, event, _event_job(event, np.asarray(event_irs), scene.ref_db, ignore_cache)))
+            emitter_counter += n
+    return jobs
+
+
+def render_audio_for_all_scene_events(scene, ignore_cache: Optional[bool] = False) -> None:
+    """synthesize.py:613-677 — all (microphone, event) renders of the scene, as ONE batched GPU call."""
+    jobs = _scene_event_jobs(scene, bool(ignore_cache))
+    start = time()
+    if jobs:
+        get_renderer().render([j for _, _, j in jobs])
+        for mic_alias, event, job in jobs:
+            _store_event_result(event, job, mic_alias)
+    logger.info(f"Rendered scene audio in {(time() - start):.2f} seconds!")
+
+
+# ---- mixdown ----------------------------------------------------------------------------------------------------------------
+def _is_ambience(obj) -> bool:
+    return hasattr(obj, "load_ambience") and hasattr(obj, "ref_db")
+
+
+def _mix_jobs_for_mic(scene, mic_alias: str, scene_index: int, prerendered: bool, event_jobs=None):
+    """SceneJob + per-event placement for one microphone (synthesize.py:327-378)."""
+    channels = max(ev.spatial_audio[mic_alias].shape[0] for ev in scene.events.values()) if prerendered else \
+        max(j.n_channels for j in event_jobs)
+    total = scene_samples(scene.duration, scene.sample_rate)
+    ambs, dbs = [], []
+    if len(scene.ambience) > 0:
+        for ambience in scene.ambience.values():
+            if not _is_ambience(ambience):
+                raise TypeError(f"Expected scene ambient noise to be of type Ambience, but got {type(ambience)}!")
+            noise = ambience.load_ambience(normalize=True)
+            if noise.shape != (channels, total):
+                raise ValueError(
+                    f"Scene ambient noise does not match expected shape. "
+                    f"Expected {(channels, total)}, but got {noise.shape}."
+                )
+            ambs.append(_as_f32(noise))
+            dbs.append(float(ambience.ref_db))
+    sjob = SceneJob(n_channels=channels, n_samples=total, ambience=ambs, ambience_ref_db=dbs)
+    placements = []
+    for event in scene.events.values():
+        s0, s1 = event_slice(event.scene_start, event.scene_end, scene.sample_rate, total)
+        if s1 <= s0:
+            logger.warning(f"Skipping event due to invalid slice: start={s0}, end={s1}")
+        placements.append((event, s0, s1))
+    return sjob, placements
+
+
+def _store_padded(event, mic_alias, spatial, s0, s1, channels, total, dry) -> None:
+    """Per-event zero-padded copies (synthesize.py:381-395)."""
+    n = s1 - s0
+    padded = np.zeros((channels, total), dtype=np.float32)
+    take = min(n, spatial.shape[1])
+    padded[:, s0:s0 + take] += spatial[:, :take]
+    event._spatial_audio_padded[mic_alias] = padded
+    if dry is not None:
+        dpad = np.zeros(total, dtype=np.float32)
+        take = min(n, dry.shape[0])
+        dpad[s0:s0 + take] += dry[:take]
+        event._spatial_audio_dry_padded[mic_alias] = dpad
+
+
+def generate_scene_audio_from_events(scene) -> None:
+    """synthesize.py:314-401 — mixes the already rendered `event.spatial_audio` of every microphone with the
+    ambience into `scene.audio[mic]` (float32), and stores the per-event padded copies."""
+    mics = list(scene.state.microphones.keys())
+    jobs, sjobs, per_mic = [], [], []
+    for mi, mic_alias in enumerate(mics):
+        sjob, placements = _mix_jobs_for_mic(scene, mic_alias, mi, True)
+        sjobs.append(sjob)
+        per_mic.append(placements)
+        for event, s0, s1 in placements:
+            if s1 <= s0:
+                continue
+            sp = event.spatial_audio[mic_alias]
+            if sp.shape[0] != sjob.n_channels:
+                raise ValueError(
+                    f"operands could not be broadcast together with shapes {(sjob.n_channels, s1 - s0)} {sp.shape}")
+            jobs.append(EventJob(spatial=_as_f32(sp), n_channels=sp.shape[0], prerendered=True, scene=mi,
+                                 scene_start=s0, scene_end=s1))
+    get_renderer().render(jobs, sjobs)
+    for mic_alias, sjob, placements in zip(mics, sjobs, per_mic):
+        for event, s0, s1 in placements:
+            if s1 <= s0:
+                continue
+            _store_padded(event, mic_alias, event.spatial_audio[mic_alias], s0, s1, sjob.n_channels, sjob.n_samples,
+                          event._spatial_audio_dry.get(mic_alias))
+        _valid_audio(sjob.mix)
+        _validate_shape(sjob.mix.shape, (sjob.n_channels, sjob.n_samples))
+        scene.audio[mic_alias] = sjob.mix
+
+
+# ---- batch entry: many scenes, render + mix in one GPU call ----------------------------------------------------------------
+def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1, store_padded: bool = True) -> None:
+    """Renders and mixes a whole batch of Scene objects with one `alr_render` call (events are rendered and mixed
+    on the device without a host round trip). Equivalent to calling `render_audio_for_all_scene_events(scene,
+    ignore_cache)` and `generate_scene_audio_from_events(scene)` on every scene."""
+    all_jobs: List[EventJob] = []
+    all_scenes: List[SceneJob] = []
+    book = []
+    for scene in scenes:
+        ev_jobs = _scene_event_jobs(scene, ignore_cache)
+        by_key = {(m, id(e)): j for m, e, j in ev_jobs}
+        for mic_alias in scene.state.microphones.keys():
+            mic_jobs = []
+            for event in scene.events.values():
+                j = by_key.get((mic_alias, id(event)))
+                if j is None:  # cached: mix the stored result
+                    sp = event.spatial_audio[mic_alias]
+                    j = EventJob(spatial=_as_f32(sp), n_channels=sp.shape[0], prerendered=True)
+                mic_jobs.append(j)
+            sjob, placements = _mix_jobs_for_mic(scene, mic_alias, len(all_scenes), False, mic_jobs)
+            for j, (event, s0, s1) in zip(mic_jobs, placements):
+                j.scene, j.scene_start, j.scene_end = len(all_scenes), s0, s1
+                if j.n_channels != sjob.n_channels and s1 > s0:
+                    raise ValueError("all events of a microphone must have the same number of channels")
+            all_jobs += mic_jobs
+            all_scenes.append(sjob)
+            book.append((scene, mic_alias, sjob, mic_jobs, placements))
+    start = time()
+    get_renderer(device).render(all_jobs, all_scenes)
+    for scene, mic_alias, sjob, mic_jobs, placements in book:
+        for j, (event, s0, s1) in zip(mic_jobs, placements):
+            if not j.prerendered:
+                _store_event_result(event, j, mic_alias)
+            if store_padded and s1 > s0:
+                _store_padded(event, mic_alias, event.spatial_audio[mic_alias], s0, s1, sjob.n_channels,
+                              sjob.n_samples, event._spatial_audio_dry.get(mic_alias))
+        _valid_audio(sjob.mix)
+        scene.audio[mic_alias] = sjob.mix
+    logger.info(f"Rendered scene audio in {(time() - start):.2f} seconds!")
+
+
+# ---- installation into the reference package -----------------------------------------------------------------------------------
+_PATCHED = ("render_event_audio", "render_audio_for_all_scene_events", "generate_scene_audio_from_events",
+            "time_invariant_convolution", "time_variant_convolution")
+_originals = {}
+
+
+def install() -> None:
+    """Rebinds the hot-path functions on `audiblelight.synthesize`. `Scene.generate` imports them at call time
+    (core.py:1828-1831), so every existing caller (tests, scripts/seld/generate_dataset.py) picks them up."""
+    import audiblelight.synthesize as ref  # noqa
+    g = globals()
+    for name in _PATCHED:
+        if name not in _originals:
+            _originals[name] = getattr(ref, name)
+        setattr(ref, name, g[name])
+
+
+def uninstall() -> None:
+    if not _originals:
+        return
+    import audiblelight.synthesize as ref  # noqa
+    for name, fn in _originals.items():
+        setattr(ref, name, fn)
+    _originals.clear()

@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — scene-seconds rendered per second on the synthesis hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scenes-per-gpu S]
+
+Workload (config.workload): configs[4] of BASELINE.json — a batch of one-minute C3-style SELD scenes with moving
+events (60 s @ 24 kHz, 4 channels, 1 s RIRs, 6 static + 3 moving events of 2-10 s, one RIR per 100 ms, Gaussian
+ambience), scene-sharded: every GPU renders `--scenes-per-gpu` scenes per step (128 by default = 1024 scenes on
+8 GPUs), weak scaling, no collective on the data path. A step = one pass of the whole hot path (RIR spectra,
+cross-fade, partitioned convolution, gains, mixdown) over the GPU's batch.
+
+Printed JSON (rank 0): `value` = whole-job scene-seconds/s with inputs resident in HBM; `e2e` = the same metric
+through the C-ABI with HOST (pinned) buffers, host<->device copies inside the timed region; `roofline` for the
+dominant kernel from CUDA events recorded on the render stream inside the timed region; `cpu_baseline` = the
+oracle port of the reference algorithm on the host cores (bounded, extrapolated sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "scene_seconds_per_second"
+UNIT = "scene-seconds/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenes-per-gpu", type=int, default=128)
+    ap.add_argument("--e2e-scenes", type=int, default=16, help="scenes per e2e step and GPU (host buffers)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="c5", choices=["c5", "c2", "c1", "c4"])
+    ap.add_argument("--cpu-workers", type=int, default=None)
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def scene_spec(workload: str, idx: int):
+    from audiblelight_b200 import workload as wl
+    return {"c5": wl.c3_scene_spec, "c2": wl.c2_scene_spec, "c1": wl.c1_scene_spec, "c4": wl.c4_scene_spec}[workload](idx)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm (oracle port; the reference is pure Python and cannot
+    travel to the GPU box) on the host cores, same metric/config; rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+    vals, last = [], None
+    spent = 0.0
+    for i in range(max(1, args.steps)):
+        last = cpu_baseline.run(n_workers=args.cpu_workers, first_scene=64 * i)
+        vals.append(last["value"])
+        spent += last["wall_s"]
+        if spent + last["wall_s"] > 150:  # keep the whole arm within a few minutes
+            break
+    value = sum(vals) / len(vals)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": 0, "ms_per_step": 1000.0 * last["wall_s"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"],
+                         "per_core": last["per_core"], "mean_scene_cpu_s": last["mean_scene_cpu_s"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, world):
+    names = {"c5": "configs[4]: batch of one-minute C3-style SELD scenes with moving events (60 s @ 24 kHz, 4 ch, "
+                   "1 s RIRs, 6 static + 3 moving events, 10 RIR/s, Gaussian ambience), scene-sharded",
+             "c2": "configs[1]: 60 s @ 24 kHz, 4 ch, 9 static events + ambience",
+             "c1": "configs[0]: one static 10 s event, 4-ch 1 s RIR",
+             "c4": "configs[3]: em64 64 ch, 48 kHz, 2 s RIRs, 5 static events"}
+    return {"workload": names[args.workload], "scenes_per_gpu": args.scenes_per_gpu,
+            "scenes_total": args.scenes_per_gpu * world, "parallelism": f"scene-sharded x{world}, no collective",
+            "cache": "inputs per step (>= 18 GB per GPU at 128 scenes) are far larger than the 126 MB L2",
+            "partition": 1024}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from audiblelight_b200 import workload as wl
+    from audiblelight_b200.renderer import Renderer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the renderer)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident inputs: scene i of the job goes to rank i % world ----------------------------------------
+    S = args.scenes_per_gpu
+    specs = [scene_spec(args.workload, rank + world * k) for k in range(S)]
+    jobs, scenes = [], []
+    for si, sp in enumerate(specs):
+        arrays, amb = wl.device_scene_arrays(sp, dev)
+        j, sj = wl.scene_jobs(sp, arrays, amb, si)
+        jobs += j
+        scenes.append(sj)
+    b_alg = sum(wl.algorithmic_bytes(sp) for sp in specs)
+    b_ir = sum(wl.ir_bytes(sp) for sp in specs)
+    scene_seconds = sum(sp.duration for sp in specs)
+    rnd = Renderer(local_rank, profiling=True)
+    packed = rnd.pack(jobs, scenes)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    for _ in range(max(args.warmup, 3)):
+        rnd.run(packed, stream)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_acc = {}
+    ev0.record()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        rnd.run(packed, stream)
+        p = rnd.profile()
+        for k, v in p.items():
+            prof_acc[k] = prof_acc.get(k, 0.0) + v
+    ev1.record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    barrier()
+    ms_per_step = elapsed_ms / args.steps
+    value = scene_seconds * world / (ms_per_step / 1000.0)
+
+    # ---- end-to-end through the C-ABI with pinned HOST buffers ------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        Se = min(args.e2e_scenes, S)
+        h_jobs, h_scenes = [], []
+        for si in range(Se):
+            sp = specs[si]
+            arrays, amb = wl.device_scene_arrays(sp, dev)
+
+            def pin(t):
+                return t.cpu().pin_memory().numpy()
+
+            arrays = [(pin(x), pin(h)) for x, h in arrays]
+            amb = pin(amb) if amb is not None else None
+            j, sj = wl.scene_jobs(sp, arrays, amb, si)
+            for e in j:
+                e.spatial = torch.empty((e.n_channels, e.audio.shape[0]), dtype=torch.float32).pin_memory().numpy()
+            sj.mix = torch.empty((sj.n_channels, sj.n_samples), dtype=torch.float32).pin_memory().numpy()
+            h_jobs += j
+            h_scenes.append(sj)
+        for _ in range(2):
+            rnd.render(h_jobs, h_scenes, stream)
+        barrier()
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        for _ in range(args.e2e_steps):
+            rnd.render(h_jobs, h_scenes, stream)  # pack + plan + H2D + kernels + D2H, synchronous
+            p = rnd.profile()
+            h2d, d2h = p["h2d_bytes"], p["d2h_bytes"]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e_ss = sum(specs[i].duration for i in range(Se)) * world
+        e2e = {"value": e2e_ss * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "scenes_per_step_per_gpu": Se, "steps": args.e2e_steps,
+               "timing": "wall clock around Renderer.render (descriptor packing, planning, pinned H2D, kernels, D2H)",
+               "pcie_gbs": (h2d + d2h) * args.e2e_steps / dt / 1e9}
+        del h_jobs, h_scenes
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (CUDA events recorded on the render stream between the launches) -------------
+    peak, peak_src = load_peaks()
+    kern_ms = {k[3:]: prof_acc[k] / args.steps for k in ("ms_ir_fft", "ms_x_fft", "ms_cmac", "ms_ifft", "ms_mix", "ms_other")}
+    dom = max(kern_ms, key=kern_ms.get)
+    # algorithmic bytes each kernel class is responsible for (DESIGN.md "Algorithmic bytes"):
+    out_bytes = sum(4 * sp.channels * e.n_audio for sp in specs for e in sp.events)
+    mix_bytes = sum(4 * sp.channels * round(sp.duration * sp.sr) * (2 if sp.ambience else 1) for sp in specs)
+    x_bytes = sum(4 * e.n_audio for sp in specs for e in sp.events)
+    alg = {"ir_fft": b_ir, "x_fft": x_bytes, "cmac": b_ir, "ifft": out_bytes, "mix": out_bytes + mix_bytes, "other": 0}
+    n_launch_dom = {"ir_fft": 1, "x_fft": 1, "cmac": 1, "ifft": 1}.get(dom, None)
+    chunks = max(1, int(prof_acc["n_chunks"] / args.steps))
+    launches_dom = chunks if n_launch_dom else None
+    dom_ms = kern_ms[dom]
+    achieved = alg[dom] / (dom_ms / 1000.0) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": {"ir_fft": "k_ir_fft", "x_fft": "k_x_fft", "cmac": "k_cmac", "ifft": "k_ifft_ola",
+                                   "mix": "k_mix+k_apply_gain+k_amb_*", "other": "misc"}[dom],
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src, "algorithmic_bytes_per_step": alg[dom], "kernel_ms_per_step": dom_ms,
+        "launches_per_step": launches_dom,
+        "kernel_share_of_step": dom_ms / ms_per_step,
+        "kernel_ms": kern_ms,
+        "pipeline": {"algorithmic_bytes_per_step": b_alg, "achieved": b_alg / (ms_per_step / 1000.0) / 1e9,
+                     "frac": b_alg / (ms_per_step / 1000.0) / 1e9 / peak,
+                     "note": "whole hot path: B_alg of SURVEY.md 8(d) / step time"},
+    }
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import cpu_baseline
+        c = cpu_baseline.run(n_workers=args.cpu_workers)
+        cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"], "sample": c["sample"],
+               "per_core": c["per_core"], "mean_scene_cpu_s": c["mean_scene_cpu_s"], "wall_s": c["wall_s"]}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded torch CUDA generator; structure from numpy "
+        "default_rng(1000+scene))",
+        "config": config_dict(args, world),
+        "clocks": sampler.summary(),
+        "e2e": e2e,
+        "gpu_launches": int(prof_acc["kernel_launches"]),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "host_ms_per_step_wall": 1000.0 * t_wall / args.steps,
+        "workspace_bytes": int(prof_acc["workspace_bytes"] / args.steps),
+        "chunks_per_step": chunks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

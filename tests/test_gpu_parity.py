@@ -166,7 +166,7 @@ def test_device_resident_matches_host(rnd):
 def test_small_workspace_chunks_give_same_result(gsc):
     from audiblelight_b200.renderer import Renderer
     spec = cases.SCENE_CASES["scene_moving_two_ambiences"]
-    r = Renderer(0, workspace_limit=1 << 20)
+    r = Renderer(0, workspace_limit=1 << 17)
     jobs, scene = gpu_util.scene_jobs(spec)
     r.render(jobs, [scene])
     assert r.profile()["n_chunks"] >= 2
