@@ -1,13 +1,20 @@
 // alr_fft.cuh — shared-memory Stockham FFT core (sm_100a), used by every spectral kernel of the renderer.
 //
-// A real block of 2P samples is transformed as one P-point complex FFT of the even/odd-packed signal plus an
-// "untangle" step (standard real-FFT trick), so the FFT that replaces scipy's pocketfft calls of the reference
-// (scipy.fft.rfft/irfft, synthesize.py:138,267 and scipy.signal.fftconvolve, :103,490) is a P = 1024 point
-// complex transform done by a group of 64 threads: Stockham autosort passes of radix 16, 16 and 4, butterflies
-// in registers, two exchanges through padded shared memory (split re/im planes, 1 pad word per 32 -> the
-// stride-16 scatter of the first pass is bank-conflict free).
+// A real block of 2P samples (P signal + P zero padding) is transformed with the negacyclic fold+twist map
+// (see below) and ONE P = 1024 point complex FFT done by a group of 64 threads: Stockham autosort passes of radix
+// 16, 16 and 4, butterflies in registers, two exchanges through shared memory.  This replaces scipy's pocketfft
+// calls of the reference (scipy.fft.rfft/irfft, synthesize.py:138,267; scipy.signal.fftconvolve, :103,490).
 //
-// Half spectra are stored PACKED: P complex values per block, bin 0 = (Re X[0], Re X[P]) (both are real).
+// Shared-memory layout: float2 elements, one pad element per 16 (index i -> i + i/16).  With 64-bit accesses the
+// hardware serves a warp as two half-warps of 16 lanes x 8 B; with this padding the stride-16 scatter of pass A
+// (17 t + k), the scatter of pass B and both gathers hit 16 distinct 8-byte bank pairs per half-warp, i.e. every
+// exchange is bank-conflict free (ncu on the first version, which used split re/im planes and 32-bit accesses,
+// showed the kernel L1TEX-bound at 96 % with 108 conflict wavefronts per transform: profiles/r01_*).
+//
+// Twiddles: only 5 table loads per thread and transform (w^1, w^2, w^4, w^8 of pass B and w_t of pass C); the rest
+// are products of at most three exact table values, so the rounding error stays ~3 ulp.
+//
+// A block spectrum is P ordinary complex values (8 KB).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,14 +24,13 @@ namespace alr {
 constexpr int kP = 1024;          // partition length in samples == complex FFT size
 constexpr int kGroup = 64;        // threads per FFT
 constexpr int kGroupsPerCta = 4;  // FFTs in flight per CTA
-constexpr int kPad = kP + kP / 32;
+constexpr int kPad = kP + kP / 16;
 
 struct FftSmem {
-  float re[kPad];
-  float im[kPad];
+  float2 d[kPad];
 };
 
-__device__ __forceinline__ int padi(int i) { return i + (i >> 5); }
+__device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -84,148 +90,123 @@ __device__ __forceinline__ constexpr int perm16(int k) { return 4 * (k & 3) + (k
 // P-point complex FFT by one 64-thread group.
 //   in : v[r] = element (t + 64 r), r = 0..15                         (t = thread index in the group)
 //   out: o[m][k] = spectrum element (t + 64 m) + 256 k, m,k = 0..3     (natural order, un-normalised)
-// tw[m] = exp(-2*pi*i*m/(2P)), m < 2P.  The caller must have a group_sync between any earlier use of `s` by
-// other threads and this call; on return the group may still be reading `s` (pass C), but only at indices that
-// the reading thread owns, so the caller may overwrite its own o-indices without a further barrier.
+// tw[m] = exp(-2*pi*i*m/P), m < P.  The caller must have a group_sync between any earlier use of `s` by other
+// threads and this call; on return the group may still be reading `s` (pass C gather), so the caller needs a
+// group_sync before the next transform scatters into `s`.
 template <bool INV>
 __device__ __forceinline__ void fft_core(float2 (&v)[16], FftSmem& s, const float2* __restrict__ tw, int t, int bar,
                                          float2 (&o)[4][4]) {
+  // twiddle seeds: issue the table loads first so that their latency hides behind pass A
+  const int tq = t & 15;
+  float2 w1 = __ldg(tw + 4 * tq), w2 = __ldg(tw + 8 * tq), w4 = __ldg(tw + 16 * tq), w8 = __ldg(tw + 32 * tq);
+  float2 wt = __ldg(tw + t);
+  if (INV) {
+    w1.y = -w1.y; w2.y = -w2.y; w4.y = -w4.y; w8.y = -w8.y; wt.y = -wt.y;
+  }
   // ---- pass A: radix 16, Ns = 1, no twiddles; scatter to 16*t + k
   dft16<INV>(v);
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    int i = padi(16 * t + k);
-    s.re[i] = v[perm16(k)].x;
-    s.im[i] = v[perm16(k)].y;
-  }
+  for (int k = 0; k < 16; ++k) s.d[padi(16 * t + k)] = v[perm16(k)];
   group_sync(bar);
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    int i = padi(t + 64 * r);
-    v[r] = make_float2(s.re[i], s.im[i]);
-  }
+  for (int r = 0; r < 16; ++r) v[r] = s.d[padi(t + 64 * r)];
   group_sync(bar);
-  // ---- pass B: radix 16, Ns = 16; twiddle exp(-2 pi i (t%16) r / 256) = tw[(t%16)*r*8]
-  const int tq = t & 15;
-#pragma unroll
-  for (int r = 1; r < 16; ++r) {
-    float2 w = __ldg(tw + tq * r * 8);
-    if (INV) w.y = -w.y;
-    v[r] = cmul(v[r], w);
+  // ---- pass B: radix 16, Ns = 16; twiddle exp(-2 pi i (t%16) r / 256) = w1^r, built from w1, w2, w4, w8
+  {
+    const float2 w3 = cmul(w1, w2), w5 = cmul(w1, w4), w6 = cmul(w2, w4), w9 = cmul(w1, w8), w10 = cmul(w2, w8),
+                 w12 = cmul(w4, w8);
+    const float2 w7 = cmul(w3, w4), w11 = cmul(w3, w8), w13 = cmul(w5, w8), w14 = cmul(w6, w8);
+    const float2 w15 = cmul(w7, w8);
+    v[1] = cmul(v[1], w1);   v[2] = cmul(v[2], w2);   v[3] = cmul(v[3], w3);   v[4] = cmul(v[4], w4);
+    v[5] = cmul(v[5], w5);   v[6] = cmul(v[6], w6);   v[7] = cmul(v[7], w7);   v[8] = cmul(v[8], w8);
+    v[9] = cmul(v[9], w9);   v[10] = cmul(v[10], w10); v[11] = cmul(v[11], w11); v[12] = cmul(v[12], w12);
+    v[13] = cmul(v[13], w13); v[14] = cmul(v[14], w14); v[15] = cmul(v[15], w15);
   }
   dft16<INV>(v);
   const int base = (t >> 4) * 256 + tq;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    int i = padi(base + 16 * k);
-    s.re[i] = v[perm16(k)].x;
-    s.im[i] = v[perm16(k)].y;
-  }
+  for (int k = 0; k < 16; ++k) s.d[padi(base + 16 * k)] = v[perm16(k)];
   group_sync(bar);
-  // ---- pass C: radix 4, Ns = 256; butterfly j = t + 64 m; twiddle exp(-2 pi i j r / 1024) = tw[2 j r]
+  // ---- pass C: radix 4, Ns = 256; butterfly j = t + 64 m; twiddle exp(-2 pi i j r / 1024) = (wt * c_m)^r,
+  //      c_m = exp(-i pi m / 8)
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     const int j = t + 64 * m;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int i = padi(j + 256 * r);
-      o[m][r] = make_float2(s.re[i], s.im[i]);
-    }
+    for (int r = 0; r < 4; ++r) o[m][r] = s.d[padi(j + 256 * r)];
   }
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
-    const int j = t + 64 * m;
-#pragma unroll
-    for (int r = 1; r < 4; ++r) {
-      float2 w = __ldg(tw + 2 * j * r);
-      if (INV) w.y = -w.y;
-      o[m][r] = cmul(o[m][r], w);
-    }
+    const float cr[4] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
+    const float ci[4] = {0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
+    const float2 cm = make_float2(cr[m], INV ? ci[m] : -ci[m]);
+    const float2 u1 = (m == 0) ? wt : cmul(wt, cm);
+    const float2 u2 = cmul(u1, u1);
+    const float2 u3 = cmul(u2, u1);
+    o[m][1] = cmul(o[m][1], u1);
+    o[m][2] = cmul(o[m][2], u2);
+    o[m][3] = cmul(o[m][3], u3);
     dft4<INV>(o[m][0], o[m][1], o[m][2], o[m][3]);
   }
 }
 
-// Forward real FFT of a zero-padded block: the caller provides the P/2 packed complex inputs
-// z[i] = (x[2i], x[2i+1]) for i = t + 64 r, r = 0..7 in v[0..7] (v[8..15] are the zero padding), and receives
-// the packed half spectrum in global memory at `spec` (P float2).
-__device__ __forceinline__ void rfft_block_to_global(float2 (&v)[16], FftSmem& s, const float2* __restrict__ tw,
-                                                     int t, int bar, float2* __restrict__ spec) {
+// exp(+i*pi*64*r/(2P)) = exp(i*pi*r/32): the r-dependent factor of the twist zeta^(t+64r), compile-time after unrolling
+__device__ __forceinline__ float2 zeta_step(int r) {
+  constexpr float c[16] = {1.0f,          0.99518472667f, 0.98078528040f, 0.95694033573f, 0.92387953251f, 0.88192126435f,
+                           0.83146961230f, 0.77301045336f, 0.70710678119f, 0.63439328416f, 0.55557023302f, 0.47139673683f,
+                           0.38268343237f, 0.29028467725f, 0.19509032202f, 0.09801714033f};
+  constexpr float sn[16] = {0.0f,          0.09801714033f, 0.19509032202f, 0.29028467725f, 0.38268343237f, 0.47139673683f,
+                            0.55557023302f, 0.63439328416f, 0.70710678119f, 0.77301045336f, 0.83146961230f, 0.88192126435f,
+                            0.92387953251f, 0.95694033573f, 0.98078528040f, 0.99518472667f};
+  return make_float2(c[r], sn[r]);
+}
+
+// ---- negacyclic ("fold + twist") block transform ---------------------------------------------------------------------
+// A real block a[0..2P) is mapped to z[n] = (a[n] + i a[n+P]) * zeta^n, zeta = exp(i pi / 2P), n < P, followed by a
+// plain P-point complex FFT.  Pointwise products of such spectra give the NEGACYCLIC convolution of the 2P-blocks,
+// which equals the linear convolution when both blocks are zero in their second half (P + P - 1 < 2P): exactly the
+// uniform-partitioned overlap-add setting.  Every one of the P bins is an ordinary complex number (no packed
+// DC/Nyquist bin, no real-FFT untangle pass), and after the inverse the first half of the block is the real part and
+// the overlap tail the imaginary part of the SAME element.
+//
+// Forward: the caller passes the real samples a[t + 64 r] in a[r] (second half implicitly zero); zt = zeta^t.
+__device__ __forceinline__ void fwd_block_to_global(const float (&a)[16], float2 zt, FftSmem& s,
+                                                    const float2* __restrict__ tw, int t, int bar,
+                                                    float2* __restrict__ spec) {
+  float2 v[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const float2 z = (r == 0) ? zt : cmul(zt, zeta_step(r));
+    v[r] = make_float2(a[r] * z.x, a[r] * z.y);
+  }
   float2 o[4][4];
   fft_core<false>(v, s, tw, t, bar, o);
 #pragma unroll
   for (int m = 0; m < 4; ++m)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int i = padi(t + 64 * m + 256 * k);  // indices owned by this thread in pass C
-      s.re[i] = o[m][k].x;
-      s.im[i] = o[m][k].y;
-    }
-  group_sync(bar);
-  // untangle: X[k] = E + W^k O, X[P-k] = conj(E - W^k O), E = (Z[k] + conj Z[P-k])/2, O = -i (Z[k] - conj Z[P-k])/2
-#pragma unroll
-  for (int m = 0; m < 8; ++m) {
-    const int k = t + 64 * m;  // 0 .. 511
-    if (k == 0) {
-      float zr = s.re[0], zi = s.im[0];
-      spec[0] = make_float2(zr + zi, zr - zi);
-      // k = P/2 pairs with itself: X[P/2] = conj(Z[P/2])
-      int ih = padi(kP / 2);
-      spec[kP / 2] = make_float2(s.re[ih], -s.im[ih]);
-    } else {
-      int i1 = padi(k), i2 = padi(kP - k);
-      float2 zk = make_float2(s.re[i1], s.im[i1]);
-      float2 zc = make_float2(s.re[i2], -s.im[i2]);
-      float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-      float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
-      float2 od = make_float2(d.y, -d.x);  // -i * d
-      float2 wo = cmul(__ldg(tw + k), od);
-      spec[k] = cadd(e, wo);
-      spec[kP - k] = cconj(csub(e, wo));
-    }
-  }
-  group_sync(bar);  // smem free for the next transform
+    for (int k = 0; k < 4; ++k) spec[t + 64 * m + 256 * k] = o[m][k];
+  group_sync(bar);  // pass-C gathers done before the next transform's scatter
 }
 
-// Inverse of the above: packed half spectrum (global) -> o[m][k] holding complex z[(t+64m) + 256k] with
-// real block sample 2i = Re z[i], 2i+1 = Im z[i]; un-normalised (scale by 1/(2P) for a true inverse).
-__device__ __forceinline__ void irfft_block_from_global(const float2* __restrict__ spec, FftSmem& s,
-                                                        const float2* __restrict__ tw, int t, int bar,
-                                                        float2 (&o)[4][4]) {
-#pragma unroll
-  for (int m = 0; m < 8; ++m) {
-    const int k = t + 64 * m;
-    if (k == 0) {
-      float2 x0 = spec[0];
-      s.re[0] = x0.x + x0.y;
-      s.im[0] = x0.x - x0.y;
-      float2 xh = spec[kP / 2];
-      int ih = padi(kP / 2);
-      s.re[ih] = 2.f * xh.x;  // same 2x scale as the E/O sums below
-      s.im[ih] = -2.f * xh.y;
-    } else {
-      float2 a = spec[k];
-      float2 b = cconj(spec[kP - k]);
-      float2 e = cadd(a, b);
-      float2 wo = csub(a, b);
-      float2 od = cmul(wo, cconj(__ldg(tw + k)));
-      // Z[k] = E + i O ; Z[P-k] = conj(E - i O)
-      int i1 = padi(k), i2 = padi(kP - k);
-      s.re[i1] = e.x - od.y;
-      s.im[i1] = e.y + od.x;
-      s.re[i2] = e.x + od.y;
-      s.im[i2] = -(e.y - od.x);
-    }
-  }
-  group_sync(bar);
+// Inverse: spectrum (global) -> o[m][k] = un-normalised z[e] * conj(zeta^e), e = t + 64 m + 256 k:
+// real part = block sample e (first half), imaginary part = block sample P + e (overlap tail). Scale by 1/P.
+__device__ __forceinline__ void inv_block_from_global(const float2* __restrict__ spec, float2 zt, FftSmem& s,
+                                                      const float2* __restrict__ tw, int t, int bar,
+                                                      float2 (&o)[4][4]) {
   float2 v[16];
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    int i = padi(t + 64 * r);
-    v[r] = make_float2(s.re[i], s.im[i]);
-  }
-  group_sync(bar);
+  for (int r = 0; r < 16; ++r) v[r] = spec[t + 64 * r];
   fft_core<true>(v, s, tw, t, bar, o);
-  group_sync(bar);  // pass-C reads done before the next transform overwrites smem
+  const float2 ztc = cconj(zt);
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = m + 4 * k;  // e = t + 64 r
+      const float2 z = (r == 0) ? ztc : cmul(ztc, cconj(zeta_step(r)));
+      o[m][k] = cmul(o[m][k], z);
+    }
+  group_sync(bar);
 }
 
 }  // namespace alr

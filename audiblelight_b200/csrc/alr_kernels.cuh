@@ -18,7 +18,7 @@ namespace alr {
 constexpr int kCtaThreads = kGroup * kGroupsPerCta;  // 256
 constexpr int kChanGroup = 4;                        // channels per CMAC / IFFT CTA
 constexpr int kRun = 4;                              // consecutive output blocks per IFFT CTA (tail kept in registers)
-constexpr int kBinCtas = kP / (2 * kCtaThreads);     // CMAC CTAs per spectrum (each thread: 2 bins = one float4)
+constexpr int kBinCtas = kP / kCtaThreads;           // CMAC CTAs per spectrum (each thread owns one bin)
 
 enum { kGainEvent = 0, kGainNone = 1, kGainDry = 2, kGainPass = 3 };  // Pass: already rendered, only mixed
 
@@ -112,7 +112,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // (l,k) contiguously.  Also writes the partition's energy sum(h^2) for normalize_irs.
 __global__ void __launch_bounds__(kCtaThreads)
 k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, int n_tasks,
-         const float2* __restrict__ tw, float2* __restrict__ hspec, float* __restrict__ hen) {
+         const float2* __restrict__ tw, const float2* __restrict__ zeta, float2* __restrict__ hspec,
+         float* __restrict__ hen) {
   __shared__ FftSmem sm[kGroupsPerCta];
   __shared__ float s_red[kGroupsPerCta][2];
   const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
@@ -125,34 +126,22 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
   local /= ev.C;
   const int k = local % ev.K;
   const int l = local / ev.K;
-  const float* src = ev.irs + (long long)c * ev.ir_stride_c + (long long)l * ev.ir_stride_n;
+  const float* __restrict__ src = ev.irs + (long long)c * ev.ir_stride_c + (long long)l * ev.ir_stride_n;
   const int t0 = k * kP;
   const int lo = max(ev.mask_lo, t0), hi = min(min(ev.mask_hi, ev.Lh), t0 + kP);
-  float2 v[16];
+  const float2 zt = __ldg(zeta + t);
+  float a[16];
   float en = 0.f;
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(src + t0) & 7u) == 0);
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int n = t0 + 2 * (t + 64 * r);
-    float a = 0.f, b = 0.f;
-    if (vec_ok && n >= lo && n + 1 < hi) {
-      float2 p = __ldg(reinterpret_cast<const float2*>(src + n));
-      a = p.x;
-      b = p.y;
-    } else {
-      if (n >= lo && n < hi) a = __ldg(src + n);
-      if (n + 1 >= lo && n + 1 < hi) b = __ldg(src + n + 1);
-    }
-    v[r] = make_float2(a, b);
-    en = fmaf(a, a, en);
-    en = fmaf(b, b, en);
+  for (int r = 0; r < 16; ++r) {
+    const int n = t0 + t + 64 * r;
+    a[r] = (n >= lo && n < hi) ? __ldg(src + n) : 0.f;
+    en = fmaf(a[r], a[r], en);
   }
-#pragma unroll
-  for (int r = 8; r < 16; ++r) v[r] = make_float2(0.f, 0.f);
   const long long slot = ev.hslot0 + (long long)(l * ev.K + k) * ev.C + c;
   en = warp_sum(en);
   if ((t & 31) == 0) s_red[g][t >> 5] = en;
-  rfft_block_to_global(v, sm[g], tw, t, bar, hspec + slot * kP);  // contains group barriers
+  fwd_block_to_global(a, zt, sm[g], tw, t, bar, hspec + slot * kP);  // contains group barriers
   if (t == 0) hen[slot] = s_red[g][0] + s_red[g][1];
 }
 
@@ -193,7 +182,8 @@ __global__ void k_ir_scale(const EvDev* __restrict__ evs, int n_ev, const int* _
 __global__ void __launch_bounds__(kCtaThreads)
 k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, int n_tasks,
         const IrDev* __restrict__ irs, const float* __restrict__ wband, const float* __restrict__ irscale,
-        const float2* __restrict__ tw, const float* __restrict__ win, float2* __restrict__ xspec) {
+        const float2* __restrict__ tw, const float2* __restrict__ zeta, const float* __restrict__ win,
+        float2* __restrict__ xspec) {
   __shared__ FftSmem sm[kGroupsPerCta];
   const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
   const int task = blockIdx.x * kGroupsPerCta + g;
@@ -216,47 +206,43 @@ k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix,
   const int t0 = (ir.xb0 + j) * kP;
   const float sc = irscale[ev.ir0 + l];
   const float* __restrict__ x = ev.x;
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(x + t0) & 7u) == 0);
-  float s0 = 0.f, s1 = 0.f;
+  const float2 zt = __ldg(zeta + t);
+  float s_even = 0.f, s_odd = 0.f;  // sin^2(pi p / 256) for p = t and p = t + 64
   if (ev.moving) {
-    s0 = __ldg(win + 2 * t);
-    s1 = __ldg(win + 2 * t + 1);
+    s_even = __ldg(win + t);
+    s_odd = __ldg(win + t + 64);
   }
-  float2 v[16];
+  float a[16];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int n = t0 + 2 * (t + 64 * r);
-    float a = 0.f, b = 0.f;
-    if (vec_ok && n + 1 < ev.xlimit) {
-      float2 p = __ldg(reinterpret_cast<const float2*>(x + n));
-      a = p.x;
-      b = p.y;
-    } else {
-      if (n < ev.xlimit) a = __ldg(x + n);
-      if (n + 1 < ev.xlimit) b = __ldg(x + n + 1);
-    }
-    float ga = sc, gb = sc;
+  for (int r = 0; r < 16; ++r) {
+    const int n = t0 + t + 64 * r;
+    float v = (n < ev.xlimit) ? __ldg(x + n) : 0.f;
+    float gw = sc;
     if (ev.moving) {
-      const int q = (n >> 7) - ir.jmin;  // frame q and q+1 cover samples n, n+1 (n even, n % 128 <= 126)
+      const int q = (t0 >> 7) + (r >> 1) - ir.jmin;  // STFT frame of sample n (uniform over the group)
       const float w0 = (q >= 0 && q < ir.nrows) ? __ldg(wband + ir.woff + q) : 0.f;
       const float w1 = (q + 1 >= 0 && q + 1 < ir.nrows) ? __ldg(wband + ir.woff + q + 1) : 0.f;
-      ga = sc * fmaf(w1 - w0, s0, w0);  // w0 (1 - s) + w1 s
-      gb = sc * fmaf(w1 - w0, s1, w0);
+      gw = sc * fmaf(w1 - w0, (r & 1) ? s_odd : s_even, w0);  // w0 (1 - s) + w1 s
     }
-    v[r] = make_float2(a * ga, b * gb);
+    a[r] = v * gw;
   }
-#pragma unroll
-  for (int r = 8; r < 16; ++r) v[r] = make_float2(0.f, 0.f);
-  rfft_block_to_global(v, sm[g], tw, t, bar, xspec + (ev.xslot0 + local) * kP);
+  fwd_block_to_global(a, zt, sm[g], tw, t, bar, xspec + (ev.xslot0 + local) * kP);
 }
 
-// k_cmac: one CTA per (event, output block b, group of 4 capsules, half of the bins); a thread owns 2 bins.
-// Y[b,c] = sum over IRs l active for b, source blocks j of l with k = b - xb0_l - j in [0, K):  X_l[j] * H_l[k,c].
-// RIR-partition spectra are read as coalesced float4 (2 bins) loads straight from L2.
-__global__ void __launch_bounds__(kCtaThreads)
+// k_cmac: Y[b,c] = sum over IRs l, source blocks j of l and partitions k with xb0_l + j + k = b of X_l[j] * H_l[k,c].
+// One CTA per (event, run of kG consecutive output blocks, group of 4 capsules, 256 bins); a thread owns ONE bin of
+// 4 capsules for the whole run: 8 x 4 complex accumulators in registers.  Each RIR-partition spectrum value
+// H_l[k,c] is loaded once (coalesced 8-byte loads, next partition prefetched) and reused for every output block of
+// the run it contributes to; the few source spectra X_l[j] a stage needs sit in a per-thread shared-memory column
+// (dynamic index j = s + d0 - k), so the inner loop is one LDS.64 + 16 FFMA per (k, s) and has no barriers.
+constexpr int kG = 8;    // output blocks per CTA
+constexpr int kXW = 16;  // source blocks staged per thread (8 B each)
+
+__global__ void __launch_bounds__(kCtaThreads, 2)
 k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const IrDev* __restrict__ irs,
-       const int2* __restrict__ lrange, const float4* __restrict__ xspec, const float4* __restrict__ hspec,
-       float4* __restrict__ yspec) {
+       const int2* __restrict__ lrange, const float2* __restrict__ xspec, const float2* __restrict__ hspec,
+       float2* __restrict__ yspec) {
+  __shared__ float2 sx[kXW][kCtaThreads];
   const int e = find_segment(prefix, n_ev, blockIdx.x);
   const EvDev& ev = evs[e];
   int local = blockIdx.x - __ldg(prefix + e);
@@ -264,70 +250,77 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
   local /= kBinCtas;
   const int ncg = (ev.C + kChanGroup - 1) / kChanGroup;
   const int cg = local % ncg;
-  const int b = local / ncg;
+  const int run = local / ncg;
   const int c0 = cg * kChanGroup;
   const int nc = min(kChanGroup, ev.C - c0);
-  const int i = br * kCtaThreads + threadIdx.x;  // float4 index inside a spectrum (bins 2i, 2i+1)
-  const bool is_dc = (i == 0);
-  float4 acc[kChanGroup];
-  float2 dc[kChanGroup];
+  const int b0 = run * kG;
+  const int nb = min(kG, ev.B_valid - b0);
+  const int tid = threadIdx.x;
+  const int bin = br * kCtaThreads + tid;
+  const int K = ev.K, C = ev.C;
+  float2 acc[kG][kChanGroup];
 #pragma unroll
-  for (int c = 0; c < kChanGroup; ++c) {
-    acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    dc[c] = make_float2(0.f, 0.f);
-  }
-  const int2 lr = lrange[ev.blk0 + b];
-  constexpr int S = kP / 2;  // float4 per spectrum
-  for (int l = lr.x; l <= lr.y; ++l) {
+  for (int s = 0; s < kG; ++s)
+#pragma unroll
+    for (int c = 0; c < kChanGroup; ++c) acc[s][c] = make_float2(0.f, 0.f);
+  const int lmin = lrange[ev.blk0 + b0].x, lmax = lrange[ev.blk0 + b0 + nb - 1].y;
+  for (int l = lmin; l <= lmax; ++l) {
     const IrDev ir = irs[ev.ir0 + l];
-    const int d = b - ir.xb0;
-    const int j_lo = max(0, d - ev.K + 1), j_hi = min(ir.xnb - 1, d);
-    const float4* xp = xspec + (ev.xslot0 + ir.xslot) * S + i;
-    const float4* hp = hspec + (ev.hslot0 + (long long)l * ev.K * ev.C + c0) * S + i;
-#pragma unroll 2
-    for (int j = j_lo; j <= j_hi; ++j) {
-      const int k = d - j;
-      const float4 xv = __ldg(xp + (long long)j * S);
-      const float4* hk = hp + (long long)k * ev.C * S;
+    if (ir.xnb == 0) continue;
+    const int d0 = b0 - ir.xb0;  // j = s + d0 - k
+    const int k_lo = max(0, d0 - ir.xnb + 1), k_hi = min(K - 1, d0 + nb - 1);
+    if (k_lo > k_hi) continue;
+    const float2* __restrict__ xp = xspec + (ev.xslot0 + ir.xslot) * kP + bin;
+    const float2* __restrict__ hp = hspec + (ev.hslot0 + (long long)l * K * C + c0) * kP + bin;
+    const int kc_max = (ir.xnb <= kXW) ? (k_hi - k_lo + 1) : (kXW - nb + 1);
+    for (int k0 = k_lo; k0 <= k_hi; k0 += kc_max) {
+      const int k1 = min(k_hi, k0 + kc_max - 1);
+      const int j_lo = max(0, d0 - k1), j_hi = min(ir.xnb - 1, d0 + nb - 1 - k0);
+      for (int j = j_lo; j <= j_hi; ++j) sx[j - j_lo][tid] = __ldg(xp + (long long)j * kP);
+      float2 h[kChanGroup], hn[kChanGroup];
 #pragma unroll
-      for (int c = 0; c < kChanGroup; ++c) {
-        if (c < nc) {
-          const float4 hv = __ldg(hk + (long long)c * S);
-          acc[c].x = fmaf(xv.x, hv.x, acc[c].x);
-          acc[c].x = fmaf(-xv.y, hv.y, acc[c].x);
-          acc[c].y = fmaf(xv.x, hv.y, acc[c].y);
-          acc[c].y = fmaf(xv.y, hv.x, acc[c].y);
-          acc[c].z = fmaf(xv.z, hv.z, acc[c].z);
-          acc[c].z = fmaf(-xv.w, hv.w, acc[c].z);
-          acc[c].w = fmaf(xv.z, hv.w, acc[c].w);
-          acc[c].w = fmaf(xv.w, hv.z, acc[c].w);
-          if (is_dc) {  // packed bin 0 = (DC, Nyquist): two real products
-            dc[c].x = fmaf(xv.x, hv.x, dc[c].x);
-            dc[c].y = fmaf(xv.y, hv.y, dc[c].y);
+      for (int c = 0; c < kChanGroup; ++c)
+        h[c] = (c < nc) ? __ldg(hp + ((long long)k0 * C + c) * kP) : make_float2(0.f, 0.f);
+      for (int k = k0; k <= k1; ++k) {
+#pragma unroll
+        for (int c = 0; c < kChanGroup; ++c)
+          hn[c] = (c < nc && k < k1) ? __ldg(hp + ((long long)(k + 1) * C + c) * kP) : make_float2(0.f, 0.f);
+        const int jb = d0 - k - j_lo;  // smem row of s = 0
+#pragma unroll
+        for (int s = 0; s < kG; ++s) {
+          const int row = s + jb;
+          if (s < nb && row >= 0 && row <= j_hi - j_lo) {
+            const float2 xv = sx[row][tid];
+#pragma unroll
+            for (int c = 0; c < kChanGroup; ++c) {
+              acc[s][c].x = fmaf(xv.x, h[c].x, acc[s][c].x);
+              acc[s][c].x = fmaf(-xv.y, h[c].y, acc[s][c].x);
+              acc[s][c].y = fmaf(xv.x, h[c].y, acc[s][c].y);
+              acc[s][c].y = fmaf(xv.y, h[c].x, acc[s][c].y);
+            }
           }
         }
+#pragma unroll
+        for (int c = 0; c < kChanGroup; ++c) h[c] = hn[c];
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < kChanGroup; ++c) {
-    if (c < nc) {
-      if (is_dc) {
-        acc[c].x = dc[c].x;
-        acc[c].y = dc[c].y;
-      }
-      yspec[(ev.yslot0 + (long long)b * ev.C + c0 + c) * S + i] = acc[c];
-    }
-  }
+  for (int s = 0; s < kG; ++s)
+    if (s < nb)
+#pragma unroll
+      for (int c = 0; c < kChanGroup; ++c)
+        if (c < nc) yspec[(ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin] = acc[s][c];
 }
 
 // k_ifft_ola: one CTA per (event, group of 4 capsules, run of kRun output blocks); group g handles capsule c0+g.
-// Inverse FFT of Y[b], overlap-add with the tail of block b-1 (kept in registers: the thread that produces
-// tail samples of block b is the one that needs them for block b+1), scale 1/(2P), truncate to n_valid, zero
-// fill up to n_out (pad_or_truncate_audio, utils.py:667), and reduce max|y| and sum|y| per CTA.
+// Inverse transform of Y[b]; the real part of element e is sample e of the block, the imaginary part its overlap
+// tail (sample P + e), which the SAME thread adds to block b+1 — the tail never leaves registers. Scale 1/P,
+// truncate to n_valid, zero fill up to n_out (pad_or_truncate_audio, utils.py:667), reduce max|y| and sum|y|.
 __global__ void __launch_bounds__(kCtaThreads)
 k_ifft_ola(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const float2* __restrict__ tw,
-           const float2* __restrict__ yspec, float2* __restrict__ partials, int part_base) {
+           const float2* __restrict__ zeta, const float2* __restrict__ yspec, float2* __restrict__ partials,
+           int part_base) {
   __shared__ FftSmem sm[kGroupsPerCta];
   __shared__ float s_max[kCtaThreads / 32], s_sum[kCtaThreads / 32];
   const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
@@ -340,19 +333,20 @@ k_ifft_ola(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ pref
   const int c = cg * kChanGroup + g;
   float vmax = 0.f, vsum = 0.f;
   if (c < ev.C) {
-    const float inv = 1.0f / (2.0f * kP);
+    const float inv = 1.0f / kP;
+    const float2 zt = __ldg(zeta + t);
     float* __restrict__ y = ev.y + (long long)c * ev.n_out;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(y) & 7u) == 0);
-    float2 tail[4][2];
+    float tail[4][4];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) tail[m][0] = tail[m][1] = make_float2(0.f, 0.f);
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tail[m][k] = 0.f;
     const int b0 = run * kRun;
     const int b1 = min(b0 + kRun, ev.B_out);
-    for (int b = b0 - 1; b < b1; ++b) {
-      if (b < 0) continue;
+    for (int b = max(b0 - 1, 0); b < b1; ++b) {
       float2 o[4][4];
       if (b < ev.B_valid) {
-        irfft_block_from_global(yspec + (ev.yslot0 + (long long)b * ev.C + c) * kP, sm[g], tw, t, bar, o);
+        inv_block_from_global(yspec + (ev.yslot0 + (long long)b * ev.C + c) * kP, zt, sm[g], tw, t, bar, o);
       } else {
 #pragma unroll
         for (int m = 0; m < 4; ++m)
@@ -361,29 +355,21 @@ k_ifft_ola(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ pref
       }
       if (b >= b0) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int n = b * kP + 2 * (t + 64 * m + 256 * k);  // output sample index (even)
-            float a = (o[m][k].x + tail[m][k].x) * inv;
-            float bb = (o[m][k].y + tail[m][k].y) * inv;
+          for (int m = 0; m < 4; ++m) {
+            const int n = b * kP + t + 64 * m + 256 * k;
+            float a = fmaf(o[m][k].x, inv, tail[m][k]);
             if (n >= ev.n_valid) a = 0.f;
-            if (n + 1 >= ev.n_valid) bb = 0.f;
-            if (vec_ok && n + 1 < ev.n_out) {
-              *reinterpret_cast<float2*>(y + n) = make_float2(a, bb);
-            } else {
-              if (n < ev.n_out) y[n] = a;
-              if (n + 1 < ev.n_out) y[n + 1] = bb;
-            }
-            vmax = fmaxf(vmax, fmaxf(fabsf(a), fabsf(bb)));
-            vsum += fabsf(a) + fabsf(bb);
+            if (n < ev.n_out) y[n] = a;
+            vmax = fmaxf(vmax, fabsf(a));
+            vsum += fabsf(a);
           }
       }
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        tail[m][0] = o[m][2];
-        tail[m][1] = o[m][3];
-      }
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tail[m][k] = o[m][k].y * inv;
     }
   }
   vmax = warp_max(vmax);
@@ -627,41 +613,39 @@ k_mix(const SceneDev* __restrict__ scenes, const AmbDev* __restrict__ ambs, cons
 // ---- unit-test kernels for the FFT core ---------------------------------------------------------------------
 __global__ void __launch_bounds__(kCtaThreads)
 k_debug_rfft(const float* __restrict__ in, long long n_blocks, long long in_stride, int n_valid,
-             const float2* __restrict__ tw, float2* __restrict__ spec) {
+             const float2* __restrict__ tw, const float2* __restrict__ zeta, float2* __restrict__ spec) {
   __shared__ FftSmem sm[kGroupsPerCta];
   const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
   const long long blk = (long long)blockIdx.x * kGroupsPerCta + g;
   if (blk >= n_blocks) return;
   const float* src = in + blk * in_stride;
-  float2 v[16];
+  float a[16];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int n = 2 * (t + 64 * r);
-    v[r] = make_float2(n < n_valid ? src[n] : 0.f, n + 1 < n_valid ? src[n + 1] : 0.f);
+  for (int r = 0; r < 16; ++r) {
+    const int n = t + 64 * r;
+    a[r] = n < n_valid ? src[n] : 0.f;
   }
-#pragma unroll
-  for (int r = 8; r < 16; ++r) v[r] = make_float2(0.f, 0.f);
-  rfft_block_to_global(v, sm[g], tw, t, bar, spec + blk * kP);
+  fwd_block_to_global(a, __ldg(zeta + t), sm[g], tw, t, bar, spec + blk * kP);
 }
 
 __global__ void __launch_bounds__(kCtaThreads)
 k_debug_irfft(const float2* __restrict__ spec, long long n_blocks, const float2* __restrict__ tw,
-              float* __restrict__ out) {
+              const float2* __restrict__ zeta, float* __restrict__ out) {
   __shared__ FftSmem sm[kGroupsPerCta];
   const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
   const long long blk = (long long)blockIdx.x * kGroupsPerCta + g;
   if (blk >= n_blocks) return;
   float2 o[4][4];
-  irfft_block_from_global(spec + blk * kP, sm[g], tw, t, bar, o);
-  const float inv = 1.0f / (2.0f * kP);
+  inv_block_from_global(spec + blk * kP, __ldg(zeta + t), sm[g], tw, t, bar, o);
+  const float inv = 1.0f / kP;
   float* dst = out + blk * 2 * kP;
 #pragma unroll
   for (int m = 0; m < 4; ++m)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int n = 2 * (t + 64 * m + 256 * k);
+      const int n = t + 64 * m + 256 * k;
       dst[n] = o[m][k].x * inv;
-      dst[n + 1] = o[m][k].y * inv;
+      dst[kP + n] = o[m][k].y * inv;
     }
 }
 

@@ -94,7 +94,8 @@ enum ProfCat { kCatIrFft = 0, kCatXFft, kCatCmac, kCatIfft, kCatMix, kCatOther, 
 
 struct alr_context {
   int device = 0;
-  float2* d_tw = nullptr;  // exp(-2 pi i m / 2P), m < 2P
+  float2* d_tw = nullptr;    // exp(-2 pi i m / P), m < P
+  float2* d_zeta = nullptr;  // exp(+i pi t / 2P), t < 64 (twist seed of thread t)
   float* d_win = nullptr;  // sin^2(pi p / 256), p < 128
   DevBuf spec, desc, misc, arena;
   HostBuf stage, stage_out;
@@ -438,11 +439,18 @@ int prof_mark(alr_context* ctx, cudaStream_t st, int cat) {
   } while (0)
 
 int init_tables(alr_context* ctx) {
-  std::vector<float2> tw(2 * kP);
-  for (int m = 0; m < 2 * kP; ++m) {
-    double a = -2.0 * M_PI * (double)m / (double)(2 * kP);
+  std::vector<float2> tw(kP);
+  for (int m = 0; m < kP; ++m) {
+    double a = -2.0 * M_PI * (double)m / (double)kP;
     tw[m] = make_float2((float)cos(a), (float)sin(a));
   }
+  std::vector<float2> zeta(kGroup);
+  for (int t = 0; t < kGroup; ++t) {
+    double a = M_PI * (double)t / (double)(2 * kP);
+    zeta[t] = make_float2((float)cos(a), (float)sin(a));
+  }
+  CUDA_TRY(cudaMalloc(&ctx->d_zeta, zeta.size() * sizeof(float2)));
+  CUDA_TRY(cudaMemcpy(ctx->d_zeta, zeta.data(), zeta.size() * sizeof(float2), cudaMemcpyHostToDevice));
   std::vector<float> win(128);
   for (int p = 0; p < 128; ++p) {
     double s = sin(M_PI * (double)p / 256.0);
@@ -505,6 +513,7 @@ void alr_destroy(alr_context* ctx) {
   cudaDeviceSynchronize();
   if (ctx->d_tw) cudaFree(ctx->d_tw);
   if (ctx->d_win) cudaFree(ctx->d_win);
+  if (ctx->d_zeta) cudaFree(ctx->d_zeta);
   ctx->spec.release();
   ctx->desc.release();
   ctx->misc.release();
@@ -728,7 +737,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       y += ev_yslots(d);
       const int ncg = (d.C + kChanGroup - 1) / kChanGroup;
       const long long n_irfft = ev_hslots(d);
-      const long long n_cmac = (long long)d.B_valid * ncg * kBinCtas;
+      const long long n_cmac = (long long)ceil_div(d.B_valid, kG) * ncg * kBinCtas;
       const long long n_ifft = d.N > 0 ? (long long)ncg * ceil_div(d.B_out, kRun) : 0;
       if (p_irfft[i] + n_irfft > 0x7ffffff0LL || p_cmac[i] + n_cmac > 0x7ffffff0LL || p_xfft[i] + nx > 0x7ffffff0LL)
         return fail(ALR_ERR_INVALID, "chunk too large for 32-bit task indices; lower the workspace limit");
@@ -856,7 +865,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     }
     if (ch.n_irfft > 0) {
       k_ir_fft<<<ceil_div(ch.n_irfft, kGroupsPerCta), kCtaThreads, 0, st>>>(c_evs, ne, p_irfft, ch.n_irfft, ctx->d_tw,
-                                                                         d_hspec, d_hen);
+                                                                         ctx->d_zeta, d_hspec, d_hen);
       LAUNCH_CHECK(kCatIrFft);
       const int n_irs = ch.ir_end - ch.ir_begin;
       k_ir_scale<<<ceil_div((long long)n_irs * 32, 128), 128, 0, st>>>(c_evs, ne, p_ir, n_irs, d_hen, d_irscale, d_stats);
@@ -864,16 +873,15 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     }
     if (ch.n_xfft > 0) {
       k_x_fft<<<ceil_div(ch.n_xfft, kGroupsPerCta), kCtaThreads, 0, st>>>(c_evs, ne, p_xfft, ch.n_xfft, d_irs, d_wband,
-                                                                        d_irscale, ctx->d_tw, ctx->d_win, d_xspec);
+                                                                        d_irscale, ctx->d_tw, ctx->d_zeta, ctx->d_win, d_xspec);
       LAUNCH_CHECK(kCatXFft);
     }
     if (ch.n_cmac > 0) {
-      k_cmac<<<ch.n_cmac, kCtaThreads, 0, st>>>(c_evs, ne, p_cmac, d_irs, d_lrange, (const float4*)d_xspec,
-                                               (const float4*)d_hspec, (float4*)d_yspec);
+      k_cmac<<<ch.n_cmac, kCtaThreads, 0, st>>>(c_evs, ne, p_cmac, d_irs, d_lrange, d_xspec, d_hspec, d_yspec);
       LAUNCH_CHECK(kCatCmac);
     }
     if (ch.n_ifft > 0) {
-      k_ifft_ola<<<ch.n_ifft, kCtaThreads, 0, st>>>(c_evs, ne, p_ifft, ctx->d_tw, d_yspec, d_parts, ch.part_base);
+      k_ifft_ola<<<ch.n_ifft, kCtaThreads, 0, st>>>(c_evs, ne, p_ifft, ctx->d_tw, ctx->d_zeta, d_yspec, d_parts, ch.part_base);
       LAUNCH_CHECK(kCatIfft);
     }
     if (ch.n_tile > 0) {
@@ -961,7 +969,7 @@ int alr_debug_rfft(alr_context* ctx, const float* in, int64_t n_blocks, int64_t 
   CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   k_debug_rfft<<<ceil_div(n_blocks, kGroupsPerCta), kCtaThreads, 0, st>>>(in, n_blocks, in_stride, n_valid, ctx->d_tw,
-                                                                        (float2*)spec_out);
+                                                                        ctx->d_zeta, (float2*)spec_out);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(st));
   return ALR_OK;
@@ -971,7 +979,7 @@ int alr_debug_irfft(alr_context* ctx, const float* spec_in, int64_t n_blocks, fl
   if (!ctx || !spec_in || !out || n_blocks < 1) return fail(ALR_ERR_INVALID, "alr_debug_irfft: bad argument");
   CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
-  k_debug_irfft<<<ceil_div(n_blocks, kGroupsPerCta), kCtaThreads, 0, st>>>((const float2*)spec_in, n_blocks, ctx->d_tw, out);
+  k_debug_irfft<<<ceil_div(n_blocks, kGroupsPerCta), kCtaThreads, 0, st>>>((const float2*)spec_in, n_blocks, ctx->d_tw, ctx->d_zeta, out);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(st));
   return ALR_OK;

@@ -35,29 +35,38 @@ def gsc():
     return np.load(os.path.join(G, "scenes.npz"))
 
 
-# ---- FFT core ------------------------------------------------------------------------------------------------
-def _unpack(spec):
-    z = spec[..., 0].astype(np.float64) + 1j * spec[..., 1].astype(np.float64)
-    full = np.concatenate([z, np.zeros(z.shape[:-1] + (1,), dtype=complex)], axis=-1)
-    full[..., -1] = z[..., 0].imag
-    full[..., 0] = z[..., 0].real
-    return full
-
-
+# ---- FFT core (negacyclic fold+twist transform, alr_fft.cuh) ----------------------------------------------------------
 @pytest.mark.parametrize("n_valid", [1024, 1000, 1, 513])
 def test_fft_core_forward_inverse(rnd, n_valid):
     import torch
+    P = 1024
     rng = np.random.default_rng(n_valid)
     x = rng.standard_normal((37, n_valid)).astype(np.float32)
     spec = rnd.debug_rfft(torch.from_numpy(x).cuda())
-    P = 1024
-    ref = np.fft.rfft(np.pad(x.astype(np.float64), ((0, 0), (0, 2 * P - n_valid))), axis=-1)
-    got = _unpack(spec.cpu().numpy())
-    scale = np.abs(ref).max()
-    assert np.abs(got - ref).max() < 2e-6 * scale
-    back = rnd.debug_irfft(spec).cpu().numpy()
+    zeta = np.exp(1j * np.pi * np.arange(P) / (2 * P))
+    ref = np.fft.fft(np.pad(x.astype(np.float64), ((0, 0), (0, P - n_valid))) * zeta, axis=-1)
+    got = spec.cpu().numpy()
+    got = got[..., 0].astype(np.float64) + 1j * got[..., 1]
+    assert np.abs(got - ref).max() < 2e-6 * np.abs(ref).max()
+    back = rnd.debug_irfft(spec).cpu().numpy()  # (n_blocks, 2P): first half = real parts, second half = overlap tail
     assert np.abs(back[:, :n_valid] - x).max() < 2e-6 * np.abs(x).max()
     assert np.abs(back[:, n_valid:]).max() < 2e-6 * np.abs(x).max()
+
+
+def test_fft_core_block_convolution(rnd):
+    """Pointwise product of two block spectra == linear convolution of the two P-sample blocks (2P-1 samples)."""
+    import torch
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((5, 1024)).astype(np.float32)
+    b = rng.standard_normal((5, 1024)).astype(np.float32)
+    A = rnd.debug_rfft(torch.from_numpy(a).cuda())
+    B = rnd.debug_rfft(torch.from_numpy(b).cuda())
+    Ac, Bc = torch.view_as_complex(A.contiguous()), torch.view_as_complex(B.contiguous())
+    Y = torch.view_as_real(Ac * Bc).contiguous()
+    y = rnd.debug_irfft(Y).cpu().numpy()
+    for i in range(5):
+        ref = np.convolve(a[i].astype(np.float64), b[i].astype(np.float64))
+        assert np.abs(y[i, :2047] - ref).max() < 3e-6 * np.abs(ref).max()
 
 
 # ---- render_event_audio vs the reference's golden output --------------------------------------------------------
