@@ -425,11 +425,10 @@ __global__ void k_tile(const EvDev* __restrict__ evs, const int* __restrict__ li
 
 // k_event_gain: one warp per event. Follows apply_snr + db_to_multiplier literally, in double:
 //   M = max(1e-15, max|y|); y1 = y * snr / M; m = mean|y1|; S = 10^((ref_db+snr)/20) / (m + tiny); out = S * y1.
-__global__ void k_event_gain(const EvDev* __restrict__ evs, int ev_begin, int ev_end,
-                             const float2* __restrict__ partials, EvStat* __restrict__ stats,
-                             float* __restrict__ gains) {
-  const int w = ev_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (w >= ev_end) return;
+__global__ void k_event_gain(const EvDev* __restrict__ evs, int n_ev, const float2* __restrict__ partials,
+                             EvStat* __restrict__ stats, float* __restrict__ gains) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_ev) return;
   const EvDev& ev = evs[w];
   if (ev.gain_mode == kGainPass) return;
   float m = 0.f;
@@ -470,10 +469,10 @@ __global__ void k_event_gain(const EvDev* __restrict__ evs, int ev_begin, int ev
 }
 
 // k_apply_gain: y *= gain for every event of the chunk. grid = (slices, events)
-__global__ void k_apply_gain(const EvDev* __restrict__ evs, int ev_begin, const float* __restrict__ gains) {
-  const EvDev& ev = evs[ev_begin + blockIdx.y];
+__global__ void k_apply_gain(const EvDev* __restrict__ evs, const float* __restrict__ gains) {
+  const EvDev& ev = evs[blockIdx.y];
   if (ev.gain_mode == kGainNone || ev.gain_mode == kGainPass) return;
-  const float gain = gains[ev_begin + blockIdx.y];
+  const float gain = gains[blockIdx.y];
   const long long total = (long long)ev.C * ev.n_out;
   float* __restrict__ y = ev.y;
   const long long stride = (long long)gridDim.x * blockDim.x;

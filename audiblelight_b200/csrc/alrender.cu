@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -105,93 +106,124 @@ struct alr_context {
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<int, int>> ev_marks;  // (category, index of the event recorded AFTER the launch)
   size_t ev_used = 0;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 };
 
 namespace {
 
 // ---- planning ------------------------------------------------------------------------------------------------
-struct Chunk {
-  int ev_begin = 0, ev_end = 0;  // internal event range
-  int ir_begin = 0, ir_end = 0;
-  long long hslots = 0, xslots = 0, yslots = 0;
-  int n_irfft = 0, n_xfft = 0, n_cmac = 0, n_ifft = 0;
-  size_t off_irfft = 0, off_ir = 0, off_xfft = 0, off_cmac = 0, off_ifft = 0;  // byte offsets of the prefix arrays
-  size_t off_tile = 0, off_dry = 0;
-  int n_tile = 0, n_dry = 0;
-  int part_base = 0;
-  bool is_dry = false;
-};
-
-struct Blob {
-  std::vector<unsigned char> bytes;
-  size_t add(const void* src, size_t n) {
-    size_t off = (bytes.size() + 15) & ~size_t(15);
-    bytes.resize(off + n);
-    if (n) memcpy(bytes.data() + off, src, n);
-    return off;
-  }
-};
-
+// Two levels.  size_event() is a cheap pre-pass (no allocation) that validates an event and derives every size the
+// launch geometry depends on; with it the whole call can be cut into workspace-bounded chunks and every buffer can
+// be sized before any detailed planning.  plan_event_into() then writes the device descriptors of one event
+// straight into the pinned staging blob of its chunk, so a chunk can be uploaded and launched while the host is
+// already planning the next one (planning overlaps GPU execution).
 constexpr int kTileSlices = 8;
 constexpr int kGainSlices = 64;
 constexpr int kAmbSlices = 64;
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-struct Plan {
-  std::vector<EvDev> evs;      // main events [0, n_main) then dry events
-  std::vector<IrDev> irs;
-  std::vector<float> wband;
-  std::vector<int2> lrange;
-  std::vector<Chunk> chunks;
-  std::vector<SceneDev> scenes;
-  std::vector<AmbDev> ambs;
-  std::vector<MixEv> mevs;
-  int n_main = 0;
-  int n_parts = 0;
-  int n_amb_parts = 0;
-  long long max_h = 0, max_x = 0, max_y = 0;
+struct EvSize {
+  int K = 0, n_valid = 0, B_valid = 0, B_out = 0, xlimit = 0;
+  long long h = 0, xb = 0, y = 0;  // spectrum slots: H exact, X upper bound, Y exact
+  int n_ir = 0;                    // IrDev entries
+  int wband = 0;                   // upper bound of cross-fade weight floats
+  int n_blk = 0;                   // lrange entries
+  int n_irfft = 0, n_cmac = 0, n_ifft = 0, n_parts = 0;
+  bool pass = false;
 };
 
-int plan_event(const alr_event& u, int idx, EvDev& d, Plan& pl) {
-  if (u.n_irs != -1 && (!u.audio || u.n_audio < 1)) return fail(ALR_ERR_INVALID, "event %d: empty audio", idx);
+int size_event(const alr_event& u, int idx, EvSize& z) {
+  z = EvSize();
   if (u.n_channels < 1) return fail(ALR_ERR_INVALID, "event %d: n_channels must be >= 1", idx);
   if (u.n_out < 1 || !u.spatial) return fail(ALR_ERR_INVALID, "event %d: no output buffer", idx);
   if (u.n_irs < -1) return fail(ALR_ERR_INVALID, "event %d: n_irs < -1", idx);
+  if (u.n_out > 0x3fffffff) return fail(ALR_ERR_INVALID, "event %d: signal too long", idx);
   if (u.n_irs == -1) {  // pre-rendered: `spatial` is an input that is only mixed
-    memset(&d, 0, sizeof(d));
-    d.y = u.spatial;
-    d.C = u.n_channels;
-    d.n_out = (int)u.n_out;
-    d.gain_mode = kGainPass;
-    d.parent = -1;
-    d.stat = idx;
-    d.ir0 = (int)pl.irs.size();
-    d.blk0 = (int)pl.lrange.size();
-    if (u.n_channels < 1 || u.n_out < 1 || !u.spatial) return fail(ALR_ERR_INVALID, "event %d: no spatial buffer", idx);
+    z.pass = true;
     return ALR_OK;
   }
+  if (!u.audio || u.n_audio < 1) return fail(ALR_ERR_INVALID, "event %d: empty audio", idx);
   if (u.n_irs > 0 && (!u.irs || u.n_ir_samples < 1)) return fail(ALR_ERR_INVALID, "event %d: empty IRs", idx);
-  if (u.n_audio > 0x3fffffff || u.n_out > 0x3fffffff || u.n_ir_samples > 0x3fffffff)
+  if (u.n_audio > 0x3fffffff || u.n_ir_samples > 0x3fffffff)
     return fail(ALR_ERR_INVALID, "event %d: signal too long", idx);
   if (u.n_irs > 1 && (!u.ir_frames || u.n_frames < 0))
     return fail(ALR_ERR_INVALID, "event %d: moving event without ir_frames / n_frames", idx);
+  const int Lx = (int)u.n_audio, Lh = (int)u.n_ir_samples, C = u.n_channels, N = u.n_irs, n_out = (int)u.n_out;
+  if (N == 0) {
+    z.n_valid = std::min(n_out, Lx);
+    z.n_parts = kTileSlices;
+    return ALR_OK;
+  }
+  const bool moving = N > 1;
+  z.K = ceil_div(Lh, kP);
+  const long long natural = moving ? std::max<long long>(0, (long long)u.n_frames * 128 - 256) : (long long)Lx + Lh - 1;
+  z.n_valid = (int)std::min<long long>(n_out, natural);
+  z.B_valid = ceil_div(z.n_valid, kP);
+  z.B_out = ceil_div(n_out, kP);
+  z.xlimit = std::min(Lx, z.n_valid);
+  z.h = (long long)N * z.K * C;
+  z.y = (long long)z.B_valid * C;
+  z.n_ir = N;
+  z.n_blk = z.B_valid;
+  if (!moving) {
+    z.xb = ceil_div(z.xlimit, kP);
+  } else {
+    const int32_t* fr = u.ir_frames;
+    if (fr[0] < 1) return fail(ALR_ERR_INVALID, "event %d: ir_frames[0] must be >= 1", idx);
+    long long xb = 0, wb = 0;
+    for (int l = 0; l < N; ++l) {
+      if (l > 0 && fr[l] < fr[l - 1]) return fail(ALR_ERR_INVALID, "event %d: ir_frames must be non-decreasing", idx);
+      const int lo = (l > 0 ? fr[l - 1] : fr[0]) - 1, hi = (l < N - 1 ? fr[l + 1] : fr[N - 1]) - 1;
+      wb += hi - lo + 1;
+      const long long t_lo = std::max<long long>(0, 128LL * lo - 128), t_hi = std::min<long long>(z.xlimit, 128LL * hi + 128);
+      if (t_hi > t_lo) xb += (t_hi - 1) / kP - t_lo / kP + 1;
+    }
+    if (wb > 0x3fffffff) return fail(ALR_ERR_INVALID, "event %d: too many STFT frames", idx);
+    z.xb = xb;
+    z.wband = (int)wb;
+  }
+  const int ncg = (C + kChanGroup - 1) / kChanGroup;
+  const long long n_cmac = (long long)ceil_div(z.B_valid, kG) * ncg * kBinCtas;
+  const long long n_ifft = (long long)ncg * ceil_div(z.B_out, kRun);
+  if (z.h > 0x3ffffff0LL || n_cmac > 0x3ffffff0LL || z.xb > 0x3ffffff0LL)
+    return fail(ALR_ERR_INVALID, "event %d: too large for 32-bit task indices", idx);
+  z.n_irfft = (int)z.h;
+  z.n_cmac = (int)n_cmac;
+  z.n_ifft = (int)n_ifft;
+  z.n_parts = (int)n_ifft;
+  return ALR_OK;
+}
+
+// Detailed plan of one event. irs_out / wband_out / lr_out point at the event's slices of the chunk arrays; ir0, w0
+// and blk0 are the offsets of those slices inside the chunk arrays (what the kernels index with).
+// Returns the number of X slots actually used in *x_used.
+void plan_event_into(const alr_event& u, int idx, const EvSize& z, EvDev& d, IrDev* irs_out, int ir0, float* wband_out,
+                     int w0, int2* lr_out, int blk0, int* x_used) {
   memset(&d, 0, sizeof(d));
+  d.y = u.spatial;
+  d.C = u.n_channels;
+  d.n_out = (int)u.n_out;
+  d.parent = -1;
+  d.stat = idx;
+  d.ir0 = ir0;
+  d.blk0 = blk0;
+  *x_used = 0;
+  if (z.pass) {
+    d.gain_mode = kGainPass;
+    return;
+  }
   d.x = u.audio;
   d.irs = u.irs;
-  d.y = u.spatial;
   d.ir_stride_c = u.ir_stride_c;
   d.ir_stride_n = u.ir_stride_n;
   d.Lx = (int)u.n_audio;
   d.Lh = (int)u.n_ir_samples;
-  d.C = u.n_channels;
   d.N = u.n_irs;
-  d.n_out = (int)u.n_out;
   d.moving = u.n_irs > 1;
   d.normalize = u.normalize_irs != 0;
   d.gain_mode = u.gain_mode == ALR_GAIN_NONE ? kGainNone : kGainEvent;
-  d.parent = -1;
-  d.stat = idx;
   d.snr = u.snr;
   d.ref_db = u.ref_db;
   d.dry_channel = u.dry_channel;
@@ -199,221 +231,137 @@ int plan_event(const alr_event& u, int idx, EvDev& d, Plan& pl) {
   d.dry_high = u.dry_high;
   d.mask_lo = 0;
   d.mask_hi = d.Lh;
-  d.ir0 = (int)pl.irs.size();
-  d.blk0 = (int)pl.lrange.size();
-  if (d.N == 0) {
-    d.K = 0;
-    d.n_valid = std::min(d.n_out, d.Lx);
-    d.B_valid = 0;
-    d.B_out = 0;
-    d.xlimit = 0;
-    return ALR_OK;
-  }
-  d.K = ceil_div(d.Lh, kP);
-  long long natural = d.moving ? std::max<long long>(0, (long long)u.n_frames * 128 - 256)
-                               : (long long)d.Lx + d.Lh - 1;
-  d.n_valid = (int)std::min<long long>(d.n_out, natural);
-  d.B_valid = ceil_div(d.n_valid, kP);
-  d.B_out = ceil_div(d.n_out, kP);
-  d.xlimit = std::min(d.Lx, d.n_valid);
-  // ---- per-IR activity
+  d.K = z.K;
+  d.n_valid = z.n_valid;
+  d.B_valid = z.B_valid;
+  d.B_out = z.B_out;
+  d.xlimit = z.xlimit;
+  if (d.N == 0) return;
   int xslot = 0;
   if (!d.moving) {
     IrDev ir{};
-    ir.xb0 = 0;
     ir.xnb = ceil_div(d.xlimit, kP);
-    ir.xslot = 0;
     xslot = ir.xnb;
-    pl.irs.push_back(ir);
+    irs_out[0] = ir;
   } else {
     const int N = d.N;
     const int32_t* fr = u.ir_frames;
-    if (fr[0] < 1) return fail(ALR_ERR_INVALID, "event %d: ir_frames[0] must be >= 1", idx);
-    for (int l = 1; l < N; ++l)
-      if (fr[l] < fr[l - 1]) return fail(ALR_ERR_INVALID, "event %d: ir_frames must be non-decreasing", idx);
-    // banded columns of the interpolation matrix, filled with the reference's assignment order
-    std::vector<int> jmin(N), jlen(N), woff(N);
+    // banded columns of the interpolation matrix (generate_interpolation_matrix, synthesize.py:172-179), filled
+    // in the reference's assignment order; column l spans rows [fr[l-1]-1, fr[l+1]-1]
+    int off = 0;
     for (int l = 0; l < N; ++l) {
-      int lo = (l > 0 ? fr[l - 1] : fr[0]) - 1;
-      int hi = (l < N - 1 ? fr[l + 1] : fr[N - 1]) - 1;
-      jmin[l] = lo;
-      jlen[l] = hi - lo + 1;
-      woff[l] = (int)pl.wband.size();
-      pl.wband.resize(pl.wband.size() + jlen[l], 0.f);
+      const int lo = (l > 0 ? fr[l - 1] : fr[0]) - 1, hi = (l < N - 1 ? fr[l + 1] : fr[N - 1]) - 1;
+      IrDev ir{};
+      ir.woff = w0 + off;
+      ir.jmin = lo;
+      ir.nrows = hi - lo + 1;
+      irs_out[l] = ir;
+      off += ir.nrows;
     }
+    memset(wband_out, 0, (size_t)off * sizeof(float));
     for (int ni = 0; ni + 1 < N; ++ni) {
       const int r0 = fr[ni] - 1, len = fr[ni + 1] - fr[ni] + 1;
       const double step = len > 1 ? 1.0 / (double)(len - 1) : 0.0;
+      float* wa = wband_out + (irs_out[ni].woff - w0) + (r0 - irs_out[ni].jmin);
+      float* wb = wband_out + (irs_out[ni + 1].woff - w0) + (r0 - irs_out[ni + 1].jmin);
       for (int i = 0; i < len; ++i) {
-        double ratio = (len > 1 && i == len - 1) ? 1.0 : (double)i * step;  // np.linspace(0, 1, len)
-        int r = r0 + i;
-        pl.wband[woff[ni] + (r - jmin[ni])] = (float)(1.0 - ratio);
-        pl.wband[woff[ni + 1] + (r - jmin[ni + 1])] = (float)ratio;
+        const double ratio = (len > 1 && i == len - 1) ? 1.0 : (double)i * step;  // np.linspace(0, 1, len)
+        wa[i] = (float)(1.0 - ratio);
+        wb[i] = (float)ratio;
       }
     }
     for (int l = 0; l < N; ++l) {
-      IrDev ir{};
-      ir.woff = woff[l];
-      ir.jmin = jmin[l];
-      ir.nrows = jlen[l];
+      IrDev& ir = irs_out[l];
       // tighten to the non-zero rows; frame j covers samples [128 j - 128, 128 j + 128)
-      int a = 0, b = jlen[l] - 1;
-      const float* w = pl.wband.data() + woff[l];
+      int a = 0, b = ir.nrows - 1;
+      const float* w = wband_out + (ir.woff - w0);
       while (a <= b && w[a] == 0.f) ++a;
       while (b >= a && w[b] == 0.f) --b;
       ir.xslot = xslot;
       if (a <= b) {
-        long long t_lo = std::max<long long>(0, 128LL * (jmin[l] + a) - 128);
-        long long t_hi = std::min<long long>(d.xlimit, 128LL * (jmin[l] + b) + 128);
+        const long long t_lo = std::max<long long>(0, 128LL * (ir.jmin + a) - 128);
+        const long long t_hi = std::min<long long>(d.xlimit, 128LL * (ir.jmin + b) + 128);
         if (t_hi > t_lo) {
           ir.xb0 = (int)(t_lo / kP);
           ir.xnb = (int)((t_hi - 1) / kP) - ir.xb0 + 1;
         }
       }
       xslot += ir.xnb;
-      pl.irs.push_back(ir);
     }
   }
-  // ---- IR range per output block (two-pointer sweep; xb0 and xb0+xnb are non-decreasing in l)
-  {
-    const IrDev* ir = pl.irs.data() + d.ir0;
-    int lo = 0;
-    for (int b = 0; b < d.B_valid; ++b) {
-      while (lo < d.N && (ir[lo].xnb == 0 || ir[lo].xb0 + ir[lo].xnb - 1 + d.K - 1 < b)) ++lo;
-      int hi = lo - 1;
-      for (int l = lo; l < d.N && (ir[l].xnb == 0 || ir[l].xb0 <= b); ++l)
-        if (ir[l].xnb > 0) hi = l;
-      int2 r;
-      r.x = lo;
-      r.y = hi;
-      pl.lrange.push_back(r);
-    }
+  // IR range per output block (two-pointer sweep; xb0 and xb0+xnb are non-decreasing over the active IRs)
+  int lo = 0;
+  for (int b = 0; b < d.B_valid; ++b) {
+    while (lo < d.N && (irs_out[lo].xnb == 0 || irs_out[lo].xb0 + irs_out[lo].xnb - 1 + d.K - 1 < b)) ++lo;
+    int hi = lo - 1;
+    for (int l = lo; l < d.N && (irs_out[l].xnb == 0 || irs_out[l].xb0 <= b); ++l)
+      if (irs_out[l].xnb > 0) hi = l;
+    lr_out[b].x = lo;
+    lr_out[b].y = hi;
   }
-  d.xslot0 = xslot;  // temporarily: number of X slots (replaced by the chunk-local base later)
-  return ALR_OK;
+  *x_used = xslot;
 }
 
-inline long long ev_hslots(const EvDev& d) { return (long long)d.N * d.K * d.C; }
-inline long long ev_yslots(const EvDev& d) { return (long long)d.B_valid * d.C; }
+// byte layout of one chunk's descriptor blob (identical in the pinned staging buffer and on the device)
+struct Chunk {
+  int ev_begin = 0, ev_end = 0;  // range in the phase's event list
+  long long hslots = 0, xslots = 0, yslots = 0;
+  int n_ir = 0, n_wband = 0, n_blk = 0;
+  size_t off_evs = 0, off_irs = 0, off_wband = 0, off_lrange = 0;
+  size_t off_irfft = 0, off_ir = 0, off_xfft = 0, off_cmac = 0, off_ifft = 0, off_tile = 0, off_dry = 0;
+  size_t bytes = 0;  // blob size
+  size_t base = 0;   // offset of the blob in the staging / descriptor buffers
+  int part_base = 0, ir_base = 0, gain_base = 0;
+};
 
-int build_plan(const alr_event* events, int64_t n_events, const alr_scene* scenes, int64_t n_scenes, int64_t ws_limit,
-               Plan& pl) {
-  pl.n_main = (int)n_events;
-  pl.evs.resize(n_events);
-  for (int64_t i = 0; i < n_events; ++i) {
-    int rc = plan_event(events[i], (int)i, pl.evs[i], pl);
-    if (rc) return rc;
-    const alr_event& u = events[i];
-    if (u.scene >= n_scenes) return fail(ALR_ERR_INVALID, "event %d: scene index %d out of range", (int)i, u.scene);
-    if (u.scene >= 0 && scenes[u.scene].n_channels != u.n_channels)
-      return fail(ALR_ERR_INVALID, "event %d: %d channels but scene %d has %d", (int)i, u.n_channels, u.scene,
-                  scenes[u.scene].n_channels);
-  }
-  // dry / direct-path sub-events: a static mono render of IR (ref channel, 0) windowed around its peak
-  for (int64_t i = 0; i < n_events; ++i) {
-    const alr_event& u = events[i];
-    if (!u.dry || u.n_irs == -1) continue;
-    if (u.n_irs < 1) return fail(ALR_ERR_INVALID, "event %d: dry audio needs at least one IR", (int)i);
-    if (u.dry_channel < 0 || u.dry_channel >= u.n_channels)
-      return fail(ALR_ERR_INVALID, "Reference channel index out of range for IRs with %d channels", u.n_channels);
-    alr_event s = u;
-    s.irs = u.irs + (long long)u.dry_channel * u.ir_stride_c;
-    s.n_channels = 1;
-    s.n_irs = 1;
-    s.ir_frames = nullptr;
-    s.spatial = u.dry;
-    s.n_out = u.n_audio + u.n_ir_samples - 1;
-    s.dry = nullptr;
-    EvDev d;
-    int rc = plan_event(s, (int)i, d, pl);
-    if (rc) return rc;
-    d.gain_mode = kGainDry;
-    d.parent = (int)i;
-    d.stat = (int)i;
-    d.normalize = u.normalize_irs != 0;
-    pl.evs.push_back(d);
-  }
-  // ---- chunks: consecutive events whose spectra fit the workspace limit
+void layout_chunk(Chunk& ch) {
+  const int ne = ch.ev_end - ch.ev_begin;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o = align_up(o + bytes, 16);
+    return r;
+  };
+  ch.off_evs = take((size_t)ne * sizeof(EvDev));
+  ch.off_irs = take((size_t)ch.n_ir * sizeof(IrDev));
+  ch.off_wband = take((size_t)ch.n_wband * sizeof(float));
+  ch.off_lrange = take((size_t)ch.n_blk * sizeof(int2));
+  ch.off_irfft = take((size_t)(ne + 1) * sizeof(int));
+  ch.off_ir = take((size_t)(ne + 1) * sizeof(int));
+  ch.off_xfft = take((size_t)(ne + 1) * sizeof(int));
+  ch.off_cmac = take((size_t)(ne + 1) * sizeof(int));
+  ch.off_ifft = take((size_t)(ne + 1) * sizeof(int));
+  ch.off_tile = take((size_t)ne * sizeof(int));
+  ch.off_dry = take((size_t)ne * sizeof(int));
+  ch.bytes = align_up(o, 256);
+}
+
+// cuts events [0, n) into chunks whose spectra fit `ws_limit`
+void make_chunks(const std::vector<EvSize>& sz, int64_t ws_limit, std::vector<Chunk>& out) {
   const long long slot_bytes = (long long)kP * sizeof(float2);
-  const int n_all = (int)pl.evs.size();
+  const int n = (int)sz.size();
   int e = 0;
-  while (e < n_all) {
+  while (e < n) {
     Chunk ch;
     ch.ev_begin = e;
-    ch.is_dry = e >= pl.n_main;
-    ch.ir_begin = pl.evs[e].ir0;
     long long bytes = 0;
-    while (e < n_all) {
-      if (!ch.is_dry && e >= pl.n_main) break;  // dry events start their own chunk (they depend on main results)
-      EvDev& d = pl.evs[e];
-      long long h = ev_hslots(d), x = d.xslot0, y = ev_yslots(d);
-      long long add = (h + x + y) * slot_bytes;
+    while (e < n) {
+      const EvSize& z = sz[e];
+      const long long add = (z.h + z.xb + z.y) * slot_bytes;
       if (e > ch.ev_begin && bytes + add > ws_limit) break;
       bytes += add;
-      ch.hslots += h;
-      ch.xslots += x;
-      ch.yslots += y;
+      ch.hslots += z.h;
+      ch.xslots += z.xb;
+      ch.yslots += z.y;
+      ch.n_ir += z.n_ir;
+      ch.n_wband += z.wband;
+      ch.n_blk += z.n_blk;
       ++e;
     }
     ch.ev_end = e;
-    ch.ir_end = (e < n_all) ? pl.evs[e].ir0 : (int)pl.irs.size();
-    pl.chunks.push_back(ch);
+    layout_chunk(ch);
+    out.push_back(ch);
   }
-  // ---- scenes
-  pl.scenes.resize(n_scenes);
-  for (int64_t s = 0; s < n_scenes; ++s) {
-    const alr_scene& u = scenes[s];
-    if (u.n_channels < 1 || u.n_samples < 1 || !u.mix) return fail(ALR_ERR_INVALID, "scene %d: bad shape", (int)s);
-    if (u.n_ambience < 0 || (u.n_ambience > 0 && (!u.ambience || !u.ambience_ref_db)))
-      return fail(ALR_ERR_INVALID, "scene %d: bad ambience list", (int)s);
-    SceneDev& d = pl.scenes[s];
-    memset(&d, 0, sizeof(d));
-    d.mix = u.mix;
-    d.C = u.n_channels;
-    d.T = u.n_samples;
-    d.n_amb = u.n_ambience;
-    d.amb0 = (int)pl.ambs.size();
-    for (int a = 0; a < u.n_ambience; ++a) {
-      if (!u.ambience[a]) return fail(ALR_ERR_INVALID, "scene %d: null ambience %d", (int)s, a);
-      AmbDev ad;
-      memset(&ad, 0, sizeof(ad));
-      ad.data = u.ambience[a];
-      ad.n = (long long)u.n_channels * u.n_samples;
-      ad.ref_db = u.ambience_ref_db[a];
-      ad.part0 = pl.n_amb_parts;
-      ad.nparts = kAmbSlices;
-      pl.n_amb_parts += kAmbSlices;
-      pl.ambs.push_back(ad);
-    }
-  }
-  // events of each scene, in call order (== the reference's dict order)
-  {
-    std::vector<int> count(n_scenes, 0);
-    for (int64_t i = 0; i < n_events; ++i)
-      if (events[i].scene >= 0 && events[i].scene_end > events[i].scene_start) count[events[i].scene]++;
-    int off = 0;
-    for (int64_t s = 0; s < n_scenes; ++s) {
-      pl.scenes[s].ev0 = off;
-      pl.scenes[s].nev = 0;
-      off += count[s];
-    }
-    pl.mevs.resize(off);
-    for (int64_t i = 0; i < n_events; ++i) {
-      const alr_event& u = events[i];
-      if (u.scene < 0 || u.scene_end <= u.scene_start) continue;
-      if (u.scene_start < 0 || u.scene_end > scenes[u.scene].n_samples)
-        return fail(ALR_ERR_INVALID, "event %d: scene slice [%lld, %lld) outside the scene", (int)i,
-                    (long long)u.scene_start, (long long)u.scene_end);
-      SceneDev& sd = pl.scenes[u.scene];
-      MixEv& m = pl.mevs[sd.ev0 + sd.nev++];
-      m.y = u.spatial;
-      m.start = u.scene_start;
-      m.end = u.scene_end;
-      m.n_out = (int)u.n_out;
-      m.pad = 0;
-    }
-  }
-  return ALR_OK;
 }
 
 // ---- profiling helpers ---------------------------------------------------------------------------------------
@@ -462,8 +410,6 @@ int init_tables(alr_context* ctx) {
   CUDA_TRY(cudaMemcpy(ctx->d_win, win.data(), win.size() * sizeof(float), cudaMemcpyHostToDevice));
   return ALR_OK;
 }
-
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
@@ -521,6 +467,8 @@ void alr_destroy(alr_context* ctx) {
   ctx->stage.release();
   ctx->stage_out.release();
   for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
+  if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+  if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
   delete ctx;
 }
 
@@ -567,17 +515,11 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     }
   }
 
-  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
-  CUDA_TRY(cudaEventCreate(&ev_t0));
-  CUDA_TRY(cudaEventCreate(&ev_t1));
-  struct EvGuard {
-    cudaEvent_t a, b;
-    ~EvGuard() {
-      cudaEventDestroy(a);
-      cudaEventDestroy(b);
-    }
-  } ev_guard{ev_t0, ev_t1};
-  CUDA_TRY(cudaEventRecord(ev_t0, st));
+  if (!ctx->ev_t0) {
+    CUDA_TRY(cudaEventCreate(&ctx->ev_t0));
+    CUDA_TRY(cudaEventCreate(&ctx->ev_t1));
+  }
+  CUDA_TRY(cudaEventRecord(ctx->ev_t0, st));
 
   // ---- host mode: stage every buffer on the device -------------------------------------------------------------
   struct OutCopy {
@@ -710,129 +652,155 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     }
   }
 
-  // ---- plan -------------------------------------------------------------------------------------------------------
-  Plan pl;
-  {
-    int rc = build_plan(events.data(), n_events, scenes.data(), n_scenes, ctx->ws_limit, pl);
-    if (rc) return rc;
+  // ---- sizes, chunks and buffers (cheap pre-pass; no detailed planning yet) -----------------------------------------
+  const auto host_t0 = std::chrono::steady_clock::now();
+  // phase 0: the caller's events; phase 1: dry / direct-path sub-events (static mono renders of IR (ref channel, 0)
+  // windowed around its peak, compute_dry_audio synthesize.py:432-504), which depend on phase-0 results
+  std::vector<alr_event> dry_events;
+  std::vector<int> dry_parent;
+  for (int64_t i = 0; i < n_events; ++i) {
+    const alr_event& u = events[i];
+    if (u.scene >= n_scenes) return fail(ALR_ERR_INVALID, "event %d: scene index %d out of range", (int)i, u.scene);
+    if (u.scene >= 0 && scenes[u.scene].n_channels != u.n_channels)
+      return fail(ALR_ERR_INVALID, "event %d: %d channels but scene %d has %d", (int)i, u.n_channels, u.scene,
+                  scenes[u.scene].n_channels);
+    if (!u.dry || u.n_irs == -1) continue;
+    if (u.n_irs < 1) return fail(ALR_ERR_INVALID, "event %d: dry audio needs at least one IR", (int)i);
+    if (u.dry_channel < 0 || u.dry_channel >= u.n_channels)
+      return fail(ALR_ERR_INVALID, "Reference channel index out of range for IRs with %d channels", u.n_channels);
+    alr_event sdry = u;
+    sdry.irs = u.irs + (long long)u.dry_channel * u.ir_stride_c;
+    sdry.n_channels = 1;
+    sdry.n_irs = 1;
+    sdry.ir_frames = nullptr;
+    sdry.spatial = u.dry;
+    sdry.n_out = u.n_audio + u.n_ir_samples - 1;
+    sdry.dry = nullptr;
+    dry_events.push_back(sdry);
+    dry_parent.push_back((int)i);
   }
-  const int n_all = (int)pl.evs.size();
-  Blob blob;
-  // per chunk: slot bases, prefixes, part ranges
-  int part_total = 0;
-  for (Chunk& ch : pl.chunks) {
-    const int ne = ch.ev_end - ch.ev_begin;
-    std::vector<int> p_irfft(ne + 1, 0), p_ir(ne + 1, 0), p_xfft(ne + 1, 0), p_cmac(ne + 1, 0), p_ifft(ne + 1, 0);
-    std::vector<int> tiles, drys;
-    long long h = 0, x = 0, y = 0;
-    ch.part_base = part_total;
-    for (int i = 0; i < ne; ++i) {
-      EvDev& d = pl.evs[ch.ev_begin + i];
-      const long long nx = d.xslot0;  // X slot count stored by plan_event
-      d.hslot0 = h;
-      d.xslot0 = x;
-      d.yslot0 = y;
-      h += ev_hslots(d);
-      x += nx;
-      y += ev_yslots(d);
-      const int ncg = (d.C + kChanGroup - 1) / kChanGroup;
-      const long long n_irfft = ev_hslots(d);
-      const long long n_cmac = (long long)ceil_div(d.B_valid, kG) * ncg * kBinCtas;
-      const long long n_ifft = d.N > 0 ? (long long)ncg * ceil_div(d.B_out, kRun) : 0;
-      if (p_irfft[i] + n_irfft > 0x7ffffff0LL || p_cmac[i] + n_cmac > 0x7ffffff0LL || p_xfft[i] + nx > 0x7ffffff0LL)
-        return fail(ALR_ERR_INVALID, "chunk too large for 32-bit task indices; lower the workspace limit");
-      p_irfft[i + 1] = p_irfft[i] + (int)n_irfft;
-      p_ir[i + 1] = p_ir[i] + d.N;
-      p_xfft[i + 1] = p_xfft[i] + (int)nx;
-      p_cmac[i + 1] = p_cmac[i] + (int)n_cmac;
-      p_ifft[i + 1] = p_ifft[i] + (int)n_ifft;
-      if (d.N > 0) {
-        d.part0 = ch.part_base + p_ifft[i];
-        d.nparts = (int)n_ifft;
-      }
-      if (d.N == 0 && d.gain_mode != kGainPass) tiles.push_back(ch.ev_begin + i);
-      if (d.gain_mode == kGainDry) drys.push_back(ch.ev_begin + i);
+  const std::vector<alr_event>* phase_events[2] = {&events, &dry_events};
+  std::vector<EvSize> sizes[2];
+  std::vector<Chunk> chunks[2];
+  for (int ph = 0; ph < 2; ++ph) {
+    const auto& evl = *phase_events[ph];
+    sizes[ph].resize(evl.size());
+    for (size_t i = 0; i < evl.size(); ++i) {
+      int rc = size_event(evl[i], ph == 0 ? (int)i : dry_parent[i], sizes[ph][i]);
+      if (rc) return rc;
     }
-    part_total += p_ifft[ne];
-    for (int ti : tiles) {
-      pl.evs[ti].part0 = part_total;
-      pl.evs[ti].nparts = kTileSlices;
-      part_total += kTileSlices;
+    make_chunks(sizes[ph], ctx->ws_limit, chunks[ph]);
+  }
+  long long max_h = 0, max_x = 0, max_y = 0;
+  size_t blob_total = 0;
+  int part_total = 0, ir_total = 0, gain_total = 0;
+  for (int ph = 0; ph < 2; ++ph)
+    for (Chunk& ch : chunks[ph]) {
+      max_h = std::max(max_h, ch.hslots);
+      max_x = std::max(max_x, ch.xslots);
+      max_y = std::max(max_y, ch.yslots);
+      ch.base = blob_total;
+      blob_total += ch.bytes;
+      ch.part_base = part_total;
+      ch.ir_base = ir_total;
+      ch.gain_base = gain_total;
+      for (int e = ch.ev_begin; e < ch.ev_end; ++e) part_total += sizes[ph][e].n_parts;
+      ir_total += ch.n_ir;
+      gain_total += ch.ev_end - ch.ev_begin;
     }
-    ch.n_irfft = p_irfft[ne];
-    ch.n_xfft = p_xfft[ne];
-    ch.n_cmac = p_cmac[ne];
-    ch.n_ifft = p_ifft[ne];
-    ch.n_tile = (int)tiles.size();
-    ch.n_dry = (int)drys.size();
-    ch.off_irfft = blob.add(p_irfft.data(), p_irfft.size() * sizeof(int));
-    ch.off_ir = blob.add(p_ir.data(), p_ir.size() * sizeof(int));
-    ch.off_xfft = blob.add(p_xfft.data(), p_xfft.size() * sizeof(int));
-    ch.off_cmac = blob.add(p_cmac.data(), p_cmac.size() * sizeof(int));
-    ch.off_ifft = blob.add(p_ifft.data(), p_ifft.size() * sizeof(int));
-    ch.off_tile = blob.add(tiles.data(), tiles.size() * sizeof(int));
-    ch.off_dry = blob.add(drys.data(), drys.size() * sizeof(int));
-    pl.max_h = std::max(pl.max_h, h);
-    pl.max_x = std::max(pl.max_x, x);
-    pl.max_y = std::max(pl.max_y, y);
+  // ---- scene / ambience / mix descriptors (independent of the event plans) ------------------------------------------
+  std::vector<SceneDev> h_scenes(n_scenes);
+  std::vector<AmbDev> h_ambs;
+  std::vector<MixEv> h_mevs;
+  int n_amb_parts = 0;
+  for (int64_t sidx = 0; sidx < n_scenes; ++sidx) {
+    const alr_scene& u = scenes[sidx];
+    if (u.n_channels < 1 || u.n_samples < 1 || !u.mix) return fail(ALR_ERR_INVALID, "scene %d: bad shape", (int)sidx);
+    if (u.n_ambience < 0 || (u.n_ambience > 0 && (!u.ambience || !u.ambience_ref_db)))
+      return fail(ALR_ERR_INVALID, "scene %d: bad ambience list", (int)sidx);
+    SceneDev& d = h_scenes[sidx];
+    memset(&d, 0, sizeof(d));
+    d.mix = u.mix;
+    d.C = u.n_channels;
+    d.T = u.n_samples;
+    d.n_amb = u.n_ambience;
+    d.amb0 = (int)h_ambs.size();
+    for (int k = 0; k < u.n_ambience; ++k) {
+      if (!amb_ptrs[sidx][k]) return fail(ALR_ERR_INVALID, "scene %d: null ambience %d", (int)sidx, k);
+      AmbDev ad;
+      memset(&ad, 0, sizeof(ad));
+      ad.data = amb_ptrs[sidx][k];
+      ad.n = (long long)u.n_channels * u.n_samples;
+      ad.ref_db = u.ambience_ref_db[k];
+      ad.part0 = n_amb_parts;
+      ad.nparts = kAmbSlices;
+      n_amb_parts += kAmbSlices;
+      h_ambs.push_back(ad);
+    }
   }
-  pl.n_parts = part_total;
-  // ambience pointers were patched in `scenes` (host mode) — refresh AmbDev.data
   {
-    size_t k = 0;
-    for (int64_t s = 0; s < n_scenes; ++s)
-      for (int a = 0; a < scenes[s].n_ambience; ++a) pl.ambs[k++].data = amb_ptrs[s][a];
+    std::vector<int> count(n_scenes, 0);
+    for (int64_t i = 0; i < n_events; ++i)
+      if (events[i].scene >= 0 && events[i].scene_end > events[i].scene_start) count[events[i].scene]++;
+    int off = 0;
+    for (int64_t sidx = 0; sidx < n_scenes; ++sidx) {
+      h_scenes[sidx].ev0 = off;
+      h_scenes[sidx].nev = 0;
+      off += count[sidx];
+    }
+    h_mevs.resize(off);
+    for (int64_t i = 0; i < n_events; ++i) {  // call order == the reference's dict order
+      const alr_event& u = events[i];
+      if (u.scene < 0 || u.scene_end <= u.scene_start) continue;
+      if (u.scene_start < 0 || u.scene_end > scenes[u.scene].n_samples)
+        return fail(ALR_ERR_INVALID, "event %d: scene slice [%lld, %lld) outside the scene", (int)i,
+                    (long long)u.scene_start, (long long)u.scene_end);
+      SceneDev& sd = h_scenes[u.scene];
+      MixEv& m = h_mevs[sd.ev0 + sd.nev++];
+      m.y = u.spatial;
+      m.start = u.scene_start;
+      m.end = u.scene_end;
+      m.n_out = (int)u.n_out;
+      m.pad = 0;
+    }
   }
-  const size_t off_evs = blob.add(pl.evs.data(), pl.evs.size() * sizeof(EvDev));
-  const size_t off_irs = blob.add(pl.irs.data(), pl.irs.size() * sizeof(IrDev));
-  const size_t off_wband = blob.add(pl.wband.data(), pl.wband.size() * sizeof(float));
-  const size_t off_lrange = blob.add(pl.lrange.data(), pl.lrange.size() * sizeof(int2));
-  const size_t off_scenes = blob.add(pl.scenes.data(), pl.scenes.size() * sizeof(SceneDev));
-  const size_t off_ambs = blob.add(pl.ambs.data(), pl.ambs.size() * sizeof(AmbDev));
-  const size_t off_mevs = blob.add(pl.mevs.data(), pl.mevs.size() * sizeof(MixEv));
-
+  const size_t mix_off_scenes = align_up(blob_total, 256);
+  const size_t mix_off_ambs = align_up(mix_off_scenes + h_scenes.size() * sizeof(SceneDev), 16);
+  const size_t mix_off_mevs = align_up(mix_off_ambs + h_ambs.size() * sizeof(AmbDev), 16);
+  const size_t desc_total = align_up(mix_off_mevs + h_mevs.size() * sizeof(MixEv), 256) + 256;
   {
-    int rc = ctx->stage.ensure(blob.bytes.size());
+    int rc = ctx->stage.ensure(desc_total);
     if (rc) return rc;
-    rc = ctx->desc.ensure(blob.bytes.size());
+    rc = ctx->desc.ensure(desc_total);
     if (rc) return rc;
   }
-  memcpy(ctx->stage.p, blob.bytes.data(), blob.bytes.size());
-  CUDA_TRY(cudaMemcpyAsync(ctx->desc.p, ctx->stage.p, blob.bytes.size(), cudaMemcpyHostToDevice, st));
-  ctx->prof.h2d_bytes += (int64_t)blob.bytes.size();
+  char* hbase = (char*)ctx->stage.p;
   char* dbase = (char*)ctx->desc.p;
-  EvDev* d_evs = (EvDev*)(dbase + off_evs);
-  IrDev* d_irs = (IrDev*)(dbase + off_irs);
-  float* d_wband = (float*)(dbase + off_wband);
-  int2* d_lrange = (int2*)(dbase + off_lrange);
-  SceneDev* d_scenes = (SceneDev*)(dbase + off_scenes);
-  AmbDev* d_ambs = (AmbDev*)(dbase + off_ambs);
-  MixEv* d_mevs = (MixEv*)(dbase + off_mevs);
-
-  // ---- workspaces ---------------------------------------------------------------------------------------------------
+  // ---- workspaces -----------------------------------------------------------------------------------------------------
   const size_t slot_bytes = (size_t)kP * sizeof(float2);
-  const size_t spec_bytes = (size_t)(pl.max_h + pl.max_x + pl.max_y) * slot_bytes;
   {
-    int rc = ctx->spec.ensure(std::max<size_t>(spec_bytes, 16));
+    int rc = ctx->spec.ensure(std::max<size_t>((size_t)(max_h + max_x + max_y) * slot_bytes, 16));
     if (rc) return rc;
   }
   float2* d_hspec = (float2*)ctx->spec.p;
-  float2* d_xspec = d_hspec + (size_t)pl.max_h * kP;
-  float2* d_yspec = d_xspec + (size_t)pl.max_x * kP;
+  float2* d_xspec = d_hspec + (size_t)max_h * kP;
+  float2* d_yspec = d_xspec + (size_t)max_x * kP;
   size_t m_off = 0;
   auto m_take = [&](size_t bytes) {
     size_t o = m_off;
     m_off = align_up(m_off + bytes, 256);
     return o;
   };
-  const size_t mo_irscale = m_take(std::max<size_t>(pl.irs.size(), 1) * sizeof(float));
-  const size_t mo_hen = m_take(std::max<size_t>((size_t)pl.max_h, 1) * sizeof(float));
-  const size_t mo_parts = m_take(std::max<size_t>(pl.n_parts, 1) * sizeof(float2));
-  const size_t mo_gain = m_take(std::max<size_t>(n_all, 1) * sizeof(float));
+  const size_t mo_irscale = m_take(std::max<size_t>(ir_total, 1) * sizeof(float));
+  const size_t mo_hen = m_take(std::max<size_t>((size_t)max_h, 1) * sizeof(float));
+  const size_t mo_parts = m_take(std::max<size_t>(part_total, 1) * sizeof(float2));
+  const size_t mo_gain = m_take(std::max<size_t>(gain_total, 1) * sizeof(float));
   const size_t mo_stats = m_take(std::max<size_t>(n_events, 1) * sizeof(EvStat));
-  const size_t mo_amb = m_take(std::max<size_t>(pl.n_amb_parts, 1) * sizeof(float));
+  const size_t mo_amb = m_take(std::max<size_t>(n_amb_parts, 1) * sizeof(float));
   {
     int rc = ctx->misc.ensure(m_off);
+    if (rc) return rc;
+    rc = ctx->stage_out.ensure(std::max<size_t>(n_events, 1) * sizeof(EvStat));
     if (rc) return rc;
   }
   char* mbase = (char*)ctx->misc.p;
@@ -844,82 +812,148 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
   float* d_ambparts = (float*)(mbase + mo_amb);
   CUDA_TRY(cudaMemsetAsync(d_stats, 0, std::max<size_t>(n_events, 1) * sizeof(EvStat), st));
   ctx->prof.workspace_bytes = (int64_t)(ctx->spec.cap + ctx->misc.cap + ctx->desc.cap + ctx->arena.cap);
-  ctx->prof.n_chunks = (int64_t)pl.chunks.size();
+  ctx->prof.n_chunks = (int64_t)(chunks[0].size() + chunks[1].size());
   {
     int rc = prof_mark(ctx, st, kNumCat);  // start marker
     if (rc) return rc;
   }
+  double host_plan_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
 
-  // ---- launches -----------------------------------------------------------------------------------------------------
-  for (const Chunk& ch : pl.chunks) {
-    const int ne = ch.ev_end - ch.ev_begin;
-    const EvDev* c_evs = d_evs + ch.ev_begin;
-    const int* p_irfft = (const int*)(dbase + ch.off_irfft);
-    const int* p_ir = (const int*)(dbase + ch.off_ir);
-    const int* p_xfft = (const int*)(dbase + ch.off_xfft);
-    const int* p_cmac = (const int*)(dbase + ch.off_cmac);
-    const int* p_ifft = (const int*)(dbase + ch.off_ifft);
-    if (ch.n_dry > 0) {
-      k_dry_window<<<ch.n_dry, 256, 0, st>>>(d_evs, (const int*)(dbase + ch.off_dry), d_stats);
-      LAUNCH_CHECK(kCatOther);
-    }
-    if (ch.n_irfft > 0) {
-      k_ir_fft<<<ceil_div(ch.n_irfft, kGroupsPerCta), kCtaThreads, 0, st>>>(c_evs, ne, p_irfft, ch.n_irfft, ctx->d_tw,
-                                                                         ctx->d_zeta, d_hspec, d_hen);
-      LAUNCH_CHECK(kCatIrFft);
-      const int n_irs = ch.ir_end - ch.ir_begin;
-      k_ir_scale<<<ceil_div((long long)n_irs * 32, 128), 128, 0, st>>>(c_evs, ne, p_ir, n_irs, d_hen, d_irscale, d_stats);
-      LAUNCH_CHECK(kCatOther);
-    }
-    if (ch.n_xfft > 0) {
-      k_x_fft<<<ceil_div(ch.n_xfft, kGroupsPerCta), kCtaThreads, 0, st>>>(c_evs, ne, p_xfft, ch.n_xfft, d_irs, d_wband,
-                                                                        d_irscale, ctx->d_tw, ctx->d_zeta, ctx->d_win, d_xspec);
-      LAUNCH_CHECK(kCatXFft);
-    }
-    if (ch.n_cmac > 0) {
-      k_cmac<<<ch.n_cmac, kCtaThreads, 0, st>>>(c_evs, ne, p_cmac, d_irs, d_lrange, d_xspec, d_hspec, d_yspec);
-      LAUNCH_CHECK(kCatCmac);
-    }
-    if (ch.n_ifft > 0) {
-      k_ifft_ola<<<ch.n_ifft, kCtaThreads, 0, st>>>(c_evs, ne, p_ifft, ctx->d_tw, ctx->d_zeta, d_yspec, d_parts, ch.part_base);
-      LAUNCH_CHECK(kCatIfft);
-    }
-    if (ch.n_tile > 0) {
-      k_tile<<<dim3(kTileSlices, ch.n_tile), 256, 0, st>>>(d_evs, (const int*)(dbase + ch.off_tile), kTileSlices, d_parts);
-      LAUNCH_CHECK(kCatOther);
-    }
-    k_event_gain<<<ceil_div((long long)ne * 32, 128), 128, 0, st>>>(d_evs, ch.ev_begin, ch.ev_end, d_parts, d_stats, d_gain);
-    LAUNCH_CHECK(kCatMix);
-    for (int e0 = 0; e0 < ne; e0 += 32768) {
-      const int cnt = std::min(32768, ne - e0);
-      k_apply_gain<<<dim3(kGainSlices, cnt), 256, 0, st>>>(d_evs, ch.ev_begin + e0, d_gain);
+  // ---- stream the chunks: plan into pinned memory, upload, launch; the host plans chunk i+1 while the GPU runs chunk i
+  for (int ph = 0; ph < 2; ++ph) {
+    const auto& evl = *phase_events[ph];
+    for (const Chunk& ch : chunks[ph]) {
+      const auto t_plan0 = std::chrono::steady_clock::now();
+      const int ne = ch.ev_end - ch.ev_begin;
+      char* hb = hbase + ch.base;
+      EvDev* h_evs = (EvDev*)(hb + ch.off_evs);
+      IrDev* h_irs = (IrDev*)(hb + ch.off_irs);
+      float* h_wband = (float*)(hb + ch.off_wband);
+      int2* h_lr = (int2*)(hb + ch.off_lrange);
+      int* p_irfft = (int*)(hb + ch.off_irfft);
+      int* p_ir = (int*)(hb + ch.off_ir);
+      int* p_xfft = (int*)(hb + ch.off_xfft);
+      int* p_cmac = (int*)(hb + ch.off_cmac);
+      int* p_ifft = (int*)(hb + ch.off_ifft);
+      int* l_tile = (int*)(hb + ch.off_tile);
+      int* l_dry = (int*)(hb + ch.off_dry);
+      int n_tile = 0, n_dry = 0, ir_off = 0, w_off = 0, blk_off = 0, parts = ch.part_base;
+      long long hs = 0, xs = 0, ys = 0;
+      p_irfft[0] = p_ir[0] = p_xfft[0] = p_cmac[0] = p_ifft[0] = 0;
+      for (int i = 0; i < ne; ++i) {
+        const int ei = ch.ev_begin + i;
+        const EvSize& z = sizes[ph][ei];
+        EvDev& d = h_evs[i];
+        int x_used = 0;
+        plan_event_into(evl[ei], ph == 0 ? ei : dry_parent[ei], z, d, h_irs + ir_off, ir_off, h_wband + w_off, w_off,
+                        h_lr + blk_off, blk_off, &x_used);
+        if (ph == 1) {
+          d.gain_mode = kGainDry;
+          d.parent = dry_parent[ei];
+          d.normalize = events[dry_parent[ei]].normalize_irs != 0;
+          l_dry[n_dry++] = i;
+        }
+        d.hslot0 = hs;
+        d.xslot0 = xs;
+        d.yslot0 = ys;
+        d.part0 = parts;
+        d.nparts = z.n_parts;
+        hs += z.h;
+        xs += z.xb;  // the bound, so that slot bases do not depend on the detailed plan
+        ys += z.y;
+        parts += z.n_parts;
+        ir_off += z.n_ir;
+        w_off += z.wband;
+        blk_off += z.n_blk;
+        p_irfft[i + 1] = p_irfft[i] + z.n_irfft;
+        p_ir[i + 1] = p_ir[i] + z.n_ir;
+        p_xfft[i + 1] = p_xfft[i] + x_used;
+        p_cmac[i + 1] = p_cmac[i] + z.n_cmac;
+        p_ifft[i + 1] = p_ifft[i] + z.n_ifft;
+        if (!z.pass && d.N == 0) l_tile[n_tile++] = i;
+      }
+      host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
+      CUDA_TRY(cudaMemcpyAsync(dbase + ch.base, hb, ch.bytes, cudaMemcpyHostToDevice, st));
+      ctx->prof.h2d_bytes += (int64_t)ch.bytes;
+      char* db = dbase + ch.base;
+      EvDev* c_evs = (EvDev*)(db + ch.off_evs);
+      const IrDev* c_irs = (const IrDev*)(db + ch.off_irs);
+      const float* c_wband = (const float*)(db + ch.off_wband);
+      const int2* c_lr = (const int2*)(db + ch.off_lrange);
+      float* c_irscale = d_irscale + ch.ir_base;
+      float* c_gain = d_gain + ch.gain_base;
+      const int n_irfft = p_irfft[ne], n_xfft = p_xfft[ne], n_cmac = p_cmac[ne], n_ifft = p_ifft[ne], n_irs = p_ir[ne];
+      if (n_dry > 0) {
+        k_dry_window<<<n_dry, 256, 0, st>>>(c_evs, (const int*)(db + ch.off_dry), d_stats);
+        LAUNCH_CHECK(kCatOther);
+      }
+      if (n_irfft > 0) {
+        k_ir_fft<<<ceil_div(n_irfft, kGroupsPerCta), kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_irfft),
+                                                                        n_irfft, ctx->d_tw, ctx->d_zeta, d_hspec, d_hen);
+        LAUNCH_CHECK(kCatIrFft);
+        k_ir_scale<<<ceil_div((long long)n_irs * 32, 128), 128, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_ir), n_irs,
+                                                                       d_hen, c_irscale, d_stats);
+        LAUNCH_CHECK(kCatOther);
+      }
+      if (n_xfft > 0) {
+        k_x_fft<<<ceil_div(n_xfft, kGroupsPerCta), kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_xfft), n_xfft,
+                                                                       c_irs, c_wband, c_irscale, ctx->d_tw, ctx->d_zeta,
+                                                                       ctx->d_win, d_xspec);
+        LAUNCH_CHECK(kCatXFft);
+      }
+      if (n_cmac > 0) {
+        k_cmac<<<n_cmac, kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_cmac), c_irs, c_lr, d_xspec, d_hspec,
+                                              d_yspec);
+        LAUNCH_CHECK(kCatCmac);
+      }
+      if (n_ifft > 0) {
+        k_ifft_ola<<<n_ifft, kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_ifft), ctx->d_tw, ctx->d_zeta,
+                                                  d_yspec, d_parts, ch.part_base);
+        LAUNCH_CHECK(kCatIfft);
+      }
+      if (n_tile > 0) {
+        k_tile<<<dim3(kTileSlices, n_tile), 256, 0, st>>>(c_evs, (const int*)(db + ch.off_tile), kTileSlices, d_parts);
+        LAUNCH_CHECK(kCatOther);
+      }
+      k_event_gain<<<ceil_div((long long)ne * 32, 128), 128, 0, st>>>(c_evs, ne, d_parts, d_stats, c_gain);
       LAUNCH_CHECK(kCatMix);
+      for (int e0 = 0; e0 < ne; e0 += 32768) {
+        const int cnt = std::min(32768, ne - e0);
+        k_apply_gain<<<dim3(kGainSlices, cnt), 256, 0, st>>>(c_evs + e0, c_gain + e0);
+        LAUNCH_CHECK(kCatMix);
+      }
     }
   }
   if (n_scenes > 0) {
-    if (!pl.ambs.empty()) {
-      for (size_t a0 = 0; a0 < pl.ambs.size(); a0 += 32768) {
-        const int cnt = (int)std::min<size_t>(32768, pl.ambs.size() - a0);
+    memcpy(hbase + mix_off_scenes, h_scenes.data(), h_scenes.size() * sizeof(SceneDev));
+    if (!h_ambs.empty()) memcpy(hbase + mix_off_ambs, h_ambs.data(), h_ambs.size() * sizeof(AmbDev));
+    if (!h_mevs.empty()) memcpy(hbase + mix_off_mevs, h_mevs.data(), h_mevs.size() * sizeof(MixEv));
+    CUDA_TRY(cudaMemcpyAsync(dbase + mix_off_scenes, hbase + mix_off_scenes, desc_total - 256 - mix_off_scenes,
+                             cudaMemcpyHostToDevice, st));
+    ctx->prof.h2d_bytes += (int64_t)(desc_total - 256 - mix_off_scenes);
+    SceneDev* d_scenes = (SceneDev*)(dbase + mix_off_scenes);
+    AmbDev* d_ambs = (AmbDev*)(dbase + mix_off_ambs);
+    MixEv* d_mevs = (MixEv*)(dbase + mix_off_mevs);
+    if (!h_ambs.empty()) {
+      for (size_t a0 = 0; a0 < h_ambs.size(); a0 += 32768) {
+        const int cnt = (int)std::min<size_t>(32768, h_ambs.size() - a0);
         k_amb_partial<<<dim3(kAmbSlices, cnt), 256, 0, st>>>(d_ambs + a0, d_ambparts);
         LAUNCH_CHECK(kCatMix);
       }
-      k_amb_final<<<ceil_div((long long)pl.ambs.size() * 32, 128), 128, 0, st>>>(d_ambs, (int)pl.ambs.size(), d_ambparts);
+      k_amb_final<<<ceil_div((long long)h_ambs.size() * 32, 128), 128, 0, st>>>(d_ambs, (int)h_ambs.size(), d_ambparts);
       LAUNCH_CHECK(kCatMix);
     }
     long long max_t = 0;
-    for (const SceneDev& s : pl.scenes) max_t = std::max(max_t, s.T);
+    for (const SceneDev& sd : h_scenes) max_t = std::max(max_t, sd.T);
     for (int64_t s0 = 0; s0 < n_scenes; s0 += 32768) {
       const int cnt = (int)std::min<int64_t>(32768, n_scenes - s0);
       k_mix<<<dim3(ceil_div(max_t, 1024), cnt), 256, 0, st>>>(d_scenes + s0, d_ambs, d_mevs);
       LAUNCH_CHECK(kCatMix);
     }
   }
+  ctx->prof.ms_host_plan = host_plan_ms;
 
   // ---- results back ---------------------------------------------------------------------------------------------------
-  {
-    int rc = ctx->stage_out.ensure(std::max<size_t>(n_events, 1) * sizeof(EvStat));
-    if (rc) return rc;
-  }
   if (n_events > 0) {
     CUDA_TRY(cudaMemcpyAsync(ctx->stage_out.p, d_stats, n_events * sizeof(EvStat), cudaMemcpyDeviceToHost, st));
     ctx->prof.d2h_bytes += (int64_t)(n_events * sizeof(EvStat));
@@ -928,10 +962,10 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     CUDA_TRY(cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, st));
     ctx->prof.d2h_bytes += (int64_t)c.bytes;
   }
-  CUDA_TRY(cudaEventRecord(ev_t1, st));
+  CUDA_TRY(cudaEventRecord(ctx->ev_t1, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   float ms = 0.f;
-  CUDA_TRY(cudaEventElapsedTime(&ms, ev_t0, ev_t1));
+  CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
   ctx->prof.ms_total = ms;
   if (ctx->profiling && ctx->ev_marks.size() > 1) {
     double acc[kNumCat] = {0};
@@ -988,30 +1022,35 @@ int alr_debug_irfft(alr_context* ctx, const float* spec_in, int64_t n_blocks, fl
 int alr_debug_plan(const alr_event* ev, int32_t* header, int32_t* irs, int64_t irs_cap, float* wband,
                    int64_t wband_cap, int32_t* lrange, int64_t lrange_cap) {
   if (!ev || !header) return fail(ALR_ERR_INVALID, "alr_debug_plan: bad argument");
-  Plan pl;
-  EvDev d;
-  int rc = plan_event(*ev, 0, d, pl);
+  EvSize z;
+  int rc = size_event(*ev, 0, z);
   if (rc) return rc;
+  std::vector<IrDev> v_irs(std::max(z.n_ir, 1));
+  std::vector<float> v_w(std::max(z.wband, 1));
+  std::vector<int2> v_lr(std::max(z.n_blk, 1));
+  EvDev d;
+  int x_used = 0;
+  plan_event_into(*ev, 0, z, d, v_irs.data(), 0, v_w.data(), 0, v_lr.data(), 0, &x_used);
   header[0] = d.K;
   header[1] = d.B_valid;
   header[2] = d.B_out;
   header[3] = d.n_valid;
   header[4] = d.xlimit;
-  header[5] = (int32_t)pl.irs.size();
-  header[6] = (int32_t)pl.wband.size();
-  header[7] = (int32_t)pl.lrange.size();
-  if ((int64_t)pl.irs.size() * 6 > irs_cap || (int64_t)pl.wband.size() > wband_cap ||
-      (int64_t)pl.lrange.size() * 2 > lrange_cap)
+  header[5] = z.n_ir;
+  header[6] = z.wband;
+  header[7] = z.n_blk;
+  if ((int64_t)z.n_ir * 6 > irs_cap || (int64_t)z.wband > wband_cap || (int64_t)z.n_blk * 2 > lrange_cap)
     return fail(ALR_ERR_INVALID, "alr_debug_plan: output buffers too small");
-  for (size_t i = 0; i < pl.irs.size(); ++i) {
-    const IrDev& r = pl.irs[i];
+  if ((long long)x_used > z.xb) return fail(ALR_ERR_INVALID, "alr_debug_plan: X slot bound violated (%d > %lld)", x_used, z.xb);
+  for (int i = 0; i < z.n_ir; ++i) {
+    const IrDev& r = v_irs[i];
     int32_t* o = irs + 6 * i;
     o[0] = r.xb0; o[1] = r.xnb; o[2] = r.xslot; o[3] = r.woff; o[4] = r.jmin; o[5] = r.nrows;
   }
-  if (!pl.wband.empty()) memcpy(wband, pl.wband.data(), pl.wband.size() * sizeof(float));
-  for (size_t i = 0; i < pl.lrange.size(); ++i) {
-    lrange[2 * i] = pl.lrange[i].x;
-    lrange[2 * i + 1] = pl.lrange[i].y;
+  if (z.wband > 0) memcpy(wband, v_w.data(), (size_t)z.wband * sizeof(float));
+  for (int i = 0; i < z.n_blk; ++i) {
+    lrange[2 * i] = v_lr[i].x;
+    lrange[2 * i + 1] = v_lr[i].y;
   }
   return ALR_OK;
 }

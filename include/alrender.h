@@ -122,6 +122,7 @@ typedef struct alr_profile {
   double ms_ifft;           /* inverse FFT + overlap-add + reductions kernel */
   double ms_mix;            /* gain + mixdown kernels (incl. ambience reduction) */
   double ms_other;
+  double ms_host_plan;       /* host time spent planning (overlaps GPU execution from the second chunk on) */
   int64_t kernel_launches;  /* kernels launched by the call */
   int64_t h2d_bytes;
   int64_t d2h_bytes;
