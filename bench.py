@@ -185,7 +185,8 @@ def main():
 
     # ---- device-resident inputs: scene i of the job goes to rank i % world ----------------------------------------
     S = args.scenes_per_gpu
-    specs = [scene_spec(args.workload, rank + world * k) for k in range(S)]
+    from audiblelight_b200 import sharding
+    specs = [scene_spec(args.workload, i) for i in sharding.shard_scene_indices(S, rank, world)]
     jobs, scenes = [], []
     for si, sp in enumerate(specs):
         arrays, amb = wl.device_scene_arrays(sp, dev)
