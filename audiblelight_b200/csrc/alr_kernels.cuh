@@ -231,18 +231,42 @@ k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix,
 
 // k_cmac: Y[b,c] = sum over IRs l, source blocks j of l and partitions k with xb0_l + j + k = b of X_l[j] * H_l[k,c].
 // One CTA per (event, run of kG consecutive output blocks, group of 4 capsules, 256 bins); a thread owns ONE bin of
-// 4 capsules for the whole run: 8 x 4 complex accumulators in registers.  Each RIR-partition spectrum value
-// H_l[k,c] is loaded once (coalesced 8-byte loads, next partition prefetched) and reused for every output block of
-// the run it contributes to; the few source spectra X_l[j] a stage needs sit in a per-thread shared-memory column
-// (dynamic index j = s + d0 - k), so the inner loop is one LDS.64 + 16 FFMA per (k, s) and has no barriers.
-constexpr int kG = 8;    // output blocks per CTA
-constexpr int kXW = 16;  // source blocks staged per thread (8 B each)
+// 4 capsules for the whole run: 8 x 4 complex accumulators in registers.
+//  * The work of a CTA is a flat sequence of items (IR l, partition k). A PRODUCER iterator runs kStages-1 items
+//    ahead of the CONSUMER iterator and copies H_l[k, c0..c0+3][bin] with cp.async (LDGSTS, 8 B per thread and
+//    capsule, coalesced 256 B per warp) into a kStages-deep ring of per-thread shared-memory columns. Every thread
+//    reads back only what it copied itself, so cp.async.wait_group is the only synchronisation: no barriers, and
+//    the pipeline does not drain at IR boundaries. (Register prefetching could not cover the DRAM latency with the
+//    16 warps/SM that 64 accumulator registers allow: profiles/r01c_cmac_*.)
+//  * Each H value is used for every output block of the run it contributes to (<= 8 x 4 FFMA per 8 bytes).
+//  * The few source spectra X_l[j] an IR needs are pulled into L1 with prefetch.global.L1 by the producer (i.e.
+//    kStages-1 items early) and read through L1 with the dynamic index j = s + d0 - k.
+constexpr int kG = 8;       // output blocks per CTA
+constexpr int kStages = 5;  // cp.async ring depth: 5 x 4 capsules x 256 threads x 8 B = 40 KB
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct CmacHead {  // one IR as seen by one CTA (run of output blocks): built once per CTA into shared memory
+  int k_lo, k_hi;    // partitions of the IR that contribute to the run (empty when k_lo > k_hi)
+  int d0, xnb;       // source block of output s and partition k: j = s + d0 - k, valid for 0 <= j < xnb
+  long long xoff;    // float2 offset of X_l[0] from the event's X base
+  long long hoff;    // float2 offset of H_l[k_lo][c0] from the event's H base
+};
+constexpr int kMaxHeads = 64;
 
 __global__ void __launch_bounds__(kCtaThreads, 2)
 k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const IrDev* __restrict__ irs,
        const int2* __restrict__ lrange, const float2* __restrict__ xspec, const float2* __restrict__ hspec,
        float2* __restrict__ yspec) {
-  __shared__ float2 sx[kXW][kCtaThreads];
+  __shared__ float2 ring[kStages][kChanGroup][kCtaThreads];
+  __shared__ CmacHead heads[kMaxHeads];
   const int e = find_segment(prefix, n_ev, blockIdx.x);
   const EvDev& ev = evs[e];
   int local = blockIdx.x - __ldg(prefix + e);
@@ -258,52 +282,125 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
   const int tid = threadIdx.x;
   const int bin = br * kCtaThreads + tid;
   const int K = ev.K, C = ev.C;
+  const long long kstride = (long long)C * kP;  // float2 elements between consecutive partitions of one IR
+  const int lmin = lrange[ev.blk0 + b0].x, lmax = lrange[ev.blk0 + b0 + nb - 1].y;
+  const IrDev* __restrict__ irp = irs + ev.ir0;
+  const float2* __restrict__ xbase = xspec + ev.xslot0 * kP + bin;
+  const float2* __restrict__ hbase = hspec + (ev.hslot0 + c0) * kP + bin;
+  float2* const ring_t = &ring[0][0][tid];  // this thread's column: stage stride 4*256, capsule stride 256 elements
+
   float2 acc[kG][kChanGroup];
 #pragma unroll
   for (int s = 0; s < kG; ++s)
 #pragma unroll
     for (int c = 0; c < kChanGroup; ++c) acc[s][c] = make_float2(0.f, 0.f);
-  const int lmin = lrange[ev.blk0 + b0].x, lmax = lrange[ev.blk0 + b0 + nb - 1].y;
-  for (int l = lmin; l <= lmax; ++l) {
-    const IrDev ir = irs[ev.ir0 + l];
-    if (ir.xnb == 0) continue;
-    const int d0 = b0 - ir.xb0;  // j = s + d0 - k
-    const int k_lo = max(0, d0 - ir.xnb + 1), k_hi = min(K - 1, d0 + nb - 1);
-    if (k_lo > k_hi) continue;
-    const float2* __restrict__ xp = xspec + (ev.xslot0 + ir.xslot) * kP + bin;
-    const float2* __restrict__ hp = hspec + (ev.hslot0 + (long long)l * K * C + c0) * kP + bin;
-    const int kc_max = (ir.xnb <= kXW) ? (k_hi - k_lo + 1) : (kXW - nb + 1);
-    for (int k0 = k_lo; k0 <= k_hi; k0 += kc_max) {
-      const int k1 = min(k_hi, k0 + kc_max - 1);
-      const int j_lo = max(0, d0 - k1), j_hi = min(ir.xnb - 1, d0 + nb - 1 - k0);
-      for (int j = j_lo; j <= j_hi; ++j) sx[j - j_lo][tid] = __ldg(xp + (long long)j * kP);
-      float2 h[kChanGroup], hn[kChanGroup];
-#pragma unroll
-      for (int c = 0; c < kChanGroup; ++c)
-        h[c] = (c < nc) ? __ldg(hp + ((long long)k0 * C + c) * kP) : make_float2(0.f, 0.f);
-      for (int k = k0; k <= k1; ++k) {
+
+  for (int l0 = lmin; l0 <= lmax; l0 += kMaxHeads) {
+    const int n_heads = min(kMaxHeads, lmax - l0 + 1);
+    __syncthreads();  // previous window fully consumed
+    if (tid < n_heads) {
+      const int l = l0 + tid;
+      const IrDev ir = irp[l];
+      CmacHead h;
+      h.d0 = b0 - ir.xb0;
+      h.xnb = ir.xnb;
+      h.k_lo = max(0, h.d0 - ir.xnb + 1);
+      h.k_hi = ir.xnb > 0 ? min(K - 1, h.d0 + nb - 1) : -1;
+      h.xoff = (long long)ir.xslot * kP;
+      h.hoff = ((long long)l * K + h.k_lo) * kstride;
+      heads[tid] = h;
+    }
+    __syncthreads();
+
+    // ---- producer state: next (IR, partition) item whose H values get copied into the ring
+    int ph = -1, pk = 0, pk_hi = -1;
+    const float2* php = hbase;
+    bool prod_ok = true;
+    auto prod_advance = [&]() {
+      if (++pk <= pk_hi) {
+        php += kstride;
+        return;
+      }
+      while (++ph < n_heads) {
+        const CmacHead h = heads[ph];
+        if (h.k_lo <= h.k_hi) {
+          pk = h.k_lo;
+          pk_hi = h.k_hi;
+          php = hbase + h.hoff;
+          // entering an IR: pull the source spectra it needs into L1 (kStages-1 items before they are used)
+          const int j_lo = max(0, h.d0 - h.k_hi), j_hi = min(h.xnb - 1, h.d0 + nb - 1 - h.k_lo);
+          const float2* xp = xbase + h.xoff;
+          for (int j = j_lo; j <= j_hi; ++j) prefetch_l1(xp + (long long)j * kP);
+          return;
+        }
+      }
+      prod_ok = false;
+    };
+    auto produce = [&](int stage) {
+      if (prod_ok) {
+        float2* dst = ring_t + stage * (kChanGroup * kCtaThreads);
 #pragma unroll
         for (int c = 0; c < kChanGroup; ++c)
-          hn[c] = (c < nc && k < k1) ? __ldg(hp + ((long long)(k + 1) * C + c) * kP) : make_float2(0.f, 0.f);
-        const int jb = d0 - k - j_lo;  // smem row of s = 0
+          if (c < nc) cp_async8(dst + c * kCtaThreads, php + c * kP);
+        prod_advance();
+      }
+      cp_async_commit();  // (possibly empty) group: keeps the group count in step with the item count
+    };
+    // ---- consumer state
+    int ch = -1, ck = 0, ck_hi = -1, cjb = 0, cxnb = 0;
+    const float2* cxq = xbase;  // &X_l[jb][bin]: X of output s is cxq[s * kP]
+    bool cons_ok = true;
+    auto cons_advance = [&]() {
+      if (++ck <= ck_hi) {
+        --cjb;
+        cxq -= kP;
+        return;
+      }
+      while (++ch < n_heads) {
+        const CmacHead h = heads[ch];
+        if (h.k_lo <= h.k_hi) {
+          ck = h.k_lo;
+          ck_hi = h.k_hi;
+          cjb = h.d0 - h.k_lo;
+          cxnb = h.xnb;
+          cxq = xbase + h.xoff + (long long)cjb * kP;
+          return;
+        }
+      }
+      cons_ok = false;
+    };
+    prod_advance();
+    cons_advance();
 #pragma unroll
-        for (int s = 0; s < kG; ++s) {
-          const int row = s + jb;
-          if (s < nb && row >= 0 && row <= j_hi - j_lo) {
-            const float2 xv = sx[row][tid];
+    for (int i = 0; i < kStages - 1; ++i) produce(i);
+    int stage = 0;
+    while (cons_ok) {
+      produce(stage == 0 ? kStages - 1 : stage - 1);  // refill the slot consumed in the previous iteration
+      cp_async_wait<kStages - 1>();                    // the consumer's item has landed
+      const float2* src = ring_t + stage * (kChanGroup * kCtaThreads);
+      float2 h[kChanGroup];
 #pragma unroll
-            for (int c = 0; c < kChanGroup; ++c) {
-              acc[s][c].x = fmaf(xv.x, h[c].x, acc[s][c].x);
-              acc[s][c].x = fmaf(-xv.y, h[c].y, acc[s][c].x);
-              acc[s][c].y = fmaf(xv.x, h[c].y, acc[s][c].y);
-              acc[s][c].y = fmaf(xv.y, h[c].x, acc[s][c].y);
-            }
+      for (int c = 0; c < kChanGroup; ++c) h[c] = (c < nc) ? src[c * kCtaThreads] : make_float2(0.f, 0.f);
+      // outputs s with 0 <= s + jb < xnb and s < nb
+      const int s_lo = max(0, -cjb);
+      const unsigned s_cnt = (unsigned)max(0, min(nb, cxnb - cjb) - s_lo);
+#pragma unroll
+      for (int s = 0; s < kG; ++s) {
+        if ((unsigned)(s - s_lo) < s_cnt) {
+          const float2 xv = __ldg(cxq + s * kP);
+#pragma unroll
+          for (int c = 0; c < kChanGroup; ++c) {
+            acc[s][c].x = fmaf(xv.x, h[c].x, acc[s][c].x);
+            acc[s][c].x = fmaf(-xv.y, h[c].y, acc[s][c].x);
+            acc[s][c].y = fmaf(xv.x, h[c].y, acc[s][c].y);
+            acc[s][c].y = fmaf(xv.y, h[c].x, acc[s][c].y);
           }
         }
-#pragma unroll
-        for (int c = 0; c < kChanGroup; ++c) h[c] = hn[c];
       }
+      cons_advance();
+      stage = (stage + 1 == kStages) ? 0 : stage + 1;
     }
+    cp_async_wait<0>();
   }
 #pragma unroll
   for (int s = 0; s < kG; ++s)
