@@ -14,7 +14,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 
 def library_path() -> str:
-    return _LIB
+    """The library to load; ALR_LIBRARY overrides it (used to A/B kernel variants built with extra -D flags)."""
+    return os.environ.get("ALR_LIBRARY", _LIB)
 
 
 def _nvcc() -> str:
@@ -31,15 +32,18 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in _DEPS if os.path.exists(d))
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> audiblelight_b200/libalrender.so"""
-    if not force and not is_stale():
-        return _LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _LIB + ".tmp", _SRC]
+def build_library(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> audiblelight_b200/libalrender.so
+    (`defines` / `out` build a kernel variant next to it, e.g. defines=["ALR_CMAC_BINS=1"], out="variant.so")."""
+    lib = _LIB if out is None else os.path.join(_HERE, out)
+    if out is None and not force and not is_stale():
+        return lib
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines]
+    cmd += ["-o", lib + ".tmp", _SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    os.replace(_LIB + ".tmp", _LIB)
+    os.replace(lib + ".tmp", lib)
     if verbose:
         print(res.stderr)
-    return _LIB
+    return lib
