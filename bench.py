@@ -176,6 +176,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (no NCCL version banner)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -288,10 +290,21 @@ def main():
     launches_dom = chunks if n_launch_dom else None
     dom_ms = kern_ms[dom]
     achieved = alg[dom] / (dom_ms / 1000.0) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        name = {"ir_fft": "k_ir_fft", "cmac": "k_cmac"}.get(dom)
+        if name in tr and args.workload == "c5" and args.scenes_per_gpu == 128:
+            traffic = tr[name]["dram_read_bytes"] + tr[name]["dram_write_bytes"]
+    except Exception:
+        pass
+    per_launch = (lambda v: v / launches_dom) if launches_dom else (lambda v: v)
     roofline = {
         "bound": "hbm", "kernel": {"ir_fft": "k_ir_fft", "x_fft": "k_x_fft", "cmac": "k_cmac", "ifft": "k_ifft_ola",
                                    "mix": "k_mix+k_apply_gain+k_amb_*", "other": "misc"}[dom],
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "traffic_note": "DRAM bytes of one launch under ncu (profiles/ncu_traffic.json); compare with algorithmic_bytes_per_launch",
+        "algorithmic_bytes_per_launch": per_launch(alg[dom]), "kernel_us_per_launch": per_launch(dom_ms * 1000.0),
         "peak_source": peak_src, "algorithmic_bytes_per_step": alg[dom], "kernel_ms_per_step": dom_ms,
         "launches_per_step": launches_dom,
         "kernel_share_of_step": dom_ms / ms_per_step,
