@@ -107,6 +107,10 @@ struct alr_context {
   std::vector<std::pair<int, int>> ev_marks;  // (category, index of the event recorded AFTER the launch)
   size_t ev_used = 0;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  // host-mode pipeline: uploads / downloads run on their own streams and overlap the kernels of other chunks
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> sync_pool;
+  size_t sync_used = 0;
 };
 
 namespace {
@@ -467,6 +471,9 @@ void alr_destroy(alr_context* ctx) {
   ctx->stage.release();
   ctx->stage_out.release();
   for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
+  for (auto ev : ctx->sync_pool) cudaEventDestroy(ev);
+  if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+  if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
   delete ctx;
@@ -527,16 +534,20 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     const void* dev;
     size_t bytes;
   };
-  std::vector<OutCopy> out_copies;
-  if (mem_space == ALR_MEM_HOST) {
-    struct InCopy {
-      const float* host;
-      size_t off;
-      size_t bytes;
-      int kind;  // 0 linear, 1 IR block
-      int ev;
-    };
-    std::vector<InCopy> in_copies;
+  struct InCopy {
+    const float* host;
+    size_t off;
+    size_t bytes;
+    int kind;  // 0 linear, 1 IR block
+    int ev;    // event that first needs it (copies are listed in event order); -1: ambience
+  };
+  std::vector<OutCopy> out_spatial(mem_space == ALR_MEM_HOST ? n_events : 0), out_dry(mem_space == ALR_MEM_HOST ? n_events : 0);
+  std::vector<OutCopy> out_mix;
+  std::vector<InCopy> in_copies;   // event inputs, in event order
+  std::vector<InCopy> amb_copies;  // ambience layers, `ev` holds the scene index; in scene order
+  const bool host_mode = mem_space == ALR_MEM_HOST;
+  char* arena_base = nullptr;
+  if (host_mode) {
     std::unordered_map<const void*, size_t> seen;  // host pointer -> arena offset
     size_t total = 0;
     auto reserve = [&](size_t bytes) {
@@ -595,7 +606,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         if (it == seen.end()) {
           off = reserve(bytes);
           seen[p] = off;
-          in_copies.push_back({p, off, bytes, 0, -1});
+          amb_copies.push_back({p, off, bytes, 0, (int)s});
         } else {
           off = it->second;
         }
@@ -606,23 +617,10 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     int rc = ctx->arena.ensure(total);
     if (rc) return rc;
     char* base = (char*)ctx->arena.p;
-    for (const InCopy& c : in_copies) {
-      if (c.kind == 0) {
-        CUDA_TRY(cudaMemcpyAsync(base + c.off, c.host, c.bytes, cudaMemcpyHostToDevice, st));
-      } else {
-        const alr_event& u = events_in[c.ev];
-        const size_t row = (size_t)u.n_ir_samples * sizeof(float);
-        if (u.ir_stride_n == u.n_ir_samples) {
-          CUDA_TRY(cudaMemcpy2DAsync(base + c.off, row * u.n_irs, u.irs, (size_t)u.ir_stride_c * sizeof(float),
-                                     row * u.n_irs, u.n_channels, cudaMemcpyHostToDevice, st));
-        } else {
-          for (int ch = 0; ch < u.n_channels; ++ch)
-            CUDA_TRY(cudaMemcpy2DAsync(base + c.off + (size_t)ch * u.n_irs * row, row,
-                                       u.irs + (long long)ch * u.ir_stride_c, (size_t)u.ir_stride_n * sizeof(float),
-                                       row, u.n_irs, cudaMemcpyHostToDevice, st));
-        }
-      }
-      ctx->prof.h2d_bytes += (int64_t)c.bytes;
+    arena_base = base;
+    if (!ctx->s_h2d) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+      CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     }
     for (int64_t i = 0; i < n_events; ++i) {
       alr_event& u = events[i];
@@ -637,17 +635,17 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         u.ir_stride_c = (int64_t)u.n_irs * u.n_ir_samples;
       }
       size_t sp_bytes = (size_t)u.n_channels * u.n_out * sizeof(float);
-      out_copies.push_back({u.spatial, base + off_sp[i], sp_bytes});
+      out_spatial[i] = {u.spatial, base + off_sp[i], sp_bytes};
       u.spatial = (float*)(base + off_sp[i]);
       if (u.dry) {
-        out_copies.push_back({u.dry, base + off_dry[i], (size_t)(u.n_audio + u.n_ir_samples - 1) * sizeof(float)});
+        out_dry[i] = {u.dry, base + off_dry[i], (size_t)(u.n_audio + u.n_ir_samples - 1) * sizeof(float)};
         u.dry = (float*)(base + off_dry[i]);
       }
     }
     for (int64_t s = 0; s < n_scenes; ++s) {
       alr_scene& u = scenes[s];
       for (int a = 0; a < u.n_ambience; ++a) amb_ptrs[s][a] = (const float*)(base + off_amb[s][a]);
-      out_copies.push_back({u.mix, base + off_mix[s], (size_t)u.n_channels * u.n_samples * sizeof(float)});
+      out_mix.push_back({u.mix, base + off_mix[s], (size_t)u.n_channels * u.n_samples * sizeof(float)});
       u.mix = (float*)(base + off_mix[s]);
     }
   }
@@ -689,7 +687,8 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       int rc = size_event(evl[i], ph == 0 ? (int)i : dry_parent[i], sizes[ph][i]);
       if (rc) return rc;
     }
-    make_chunks(sizes[ph], ctx->ws_limit, chunks[ph]);
+    // host mode: smaller chunks give the upload / compute / download pipeline something to overlap
+    make_chunks(sizes[ph], host_mode ? std::min<int64_t>(ctx->ws_limit, (int64_t)512 << 20) : ctx->ws_limit, chunks[ph]);
   }
   long long max_h = 0, max_x = 0, max_y = 0;
   size_t blob_total = 0;
@@ -819,10 +818,173 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
   }
   double host_plan_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
 
+  // ---- host-mode copy pipeline ------------------------------------------------------------------------------------------
+  // ALR_TRACE=1: timeline of the three streams (timed events, printed relative to the start of the call)
+  const bool trace = getenv("ALR_TRACE") != nullptr;
+  struct TraceMark {
+    cudaEvent_t ev;
+    const char* what;
+    int chunk;
+  };
+  std::vector<TraceMark> trace_marks;
+  auto trace_mark = [&](cudaStream_t s_, const char* what, int chunk) {
+    if (!trace) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, s_);
+    trace_marks.push_back({ev, what, chunk});
+  };
+  ctx->sync_used = 0;
+  auto next_sync_event = [&](cudaEvent_t* out) -> int {
+    if (ctx->sync_used == ctx->sync_pool.size()) {
+      cudaEvent_t ev;
+      CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      ctx->sync_pool.push_back(ev);
+    }
+    *out = ctx->sync_pool[ctx->sync_used++];
+    return ALR_OK;
+  };
+  size_t in_cursor = 0;
+  // uploads every input first needed by an event < ev_end (copies are in event order) on the upload stream and
+  // makes the compute stream wait for them
+  size_t amb_cursor = 0;
+  auto upload_ambience_until = [&](int scene_end) -> int {
+    while (amb_cursor < amb_copies.size() && amb_copies[amb_cursor].ev < scene_end) {
+      const InCopy& c = amb_copies[amb_cursor++];
+      CUDA_TRY(cudaMemcpyAsync(arena_base + c.off, c.host, c.bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+      ctx->prof.h2d_bytes += (int64_t)c.bytes;
+    }
+    return ALR_OK;
+  };
+  auto upload_until = [&](int ev_end) -> int {
+    while (in_cursor < in_copies.size()) {
+      const InCopy& c = in_copies[in_cursor];
+      if (c.ev >= ev_end) break;
+      if (c.kind == 0) {
+        CUDA_TRY(cudaMemcpyAsync(arena_base + c.off, c.host, c.bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+      } else {
+        const alr_event& u = events_in[c.ev];
+        const size_t row = (size_t)u.n_ir_samples * sizeof(float);
+        if (u.ir_stride_n == u.n_ir_samples && u.ir_stride_c == (int64_t)u.n_irs * u.n_ir_samples) {
+          // fully contiguous (C, N, Lh): one linear copy (2-D copies do not overlap with downloads on this platform)
+          CUDA_TRY(cudaMemcpyAsync(arena_base + c.off, u.irs, c.bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+        } else if (u.ir_stride_n == u.n_ir_samples) {
+          CUDA_TRY(cudaMemcpy2DAsync(arena_base + c.off, row * u.n_irs, u.irs, (size_t)u.ir_stride_c * sizeof(float),
+                                     row * u.n_irs, u.n_channels, cudaMemcpyHostToDevice, ctx->s_h2d));
+        } else {
+          for (int chn = 0; chn < u.n_channels; ++chn)
+            CUDA_TRY(cudaMemcpy2DAsync(arena_base + c.off + (size_t)chn * u.n_irs * row, row,
+                                       u.irs + (long long)chn * u.ir_stride_c, (size_t)u.ir_stride_n * sizeof(float),
+                                       row, u.n_irs, cudaMemcpyHostToDevice, ctx->s_h2d));
+        }
+      }
+      ctx->prof.h2d_bytes += (int64_t)c.bytes;
+      ++in_cursor;
+    }
+    return ALR_OK;
+  };
+  auto compute_waits_for_uploads = [&]() -> int {
+    cudaEvent_t ev;
+    int rc = next_sync_event(&ev);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev, ctx->s_h2d));
+    CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));
+    return ALR_OK;
+  };
+  auto download_after_compute = [&](const OutCopy* list, size_t n) -> int {
+    cudaEvent_t ev;
+    int rc = next_sync_event(&ev);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev, st));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
+    for (size_t i = 0; i < n; ++i) {
+      if (!list[i].host) continue;
+      CUDA_TRY(cudaMemcpyAsync(list[i].host, list[i].dev, list[i].bytes, cudaMemcpyDeviceToHost, ctx->s_d2h));
+      ctx->prof.d2h_bytes += (int64_t)list[i].bytes;
+    }
+    return ALR_OK;
+  };
+  // ---- mixdown of scenes [s0, s1): ambience scale, then k_mix; in host mode followed by the download of the mixes
+  int scenes_mixed = 0;
+  std::vector<int> scene_last_ev(n_scenes, -1);  // a scene can be mixed once this event's chunk has been rendered
+  for (int64_t i = 0; i < n_events; ++i)
+    if (events[i].scene >= 0) scene_last_ev[events[i].scene] = (int)i;
+  // number of leading scenes whose events are all < ev_end (scenes are mixed in index order)
+  auto scenes_done_after = [&](int ev_end) -> int {
+    int sidx = scenes_mixed;
+    while (sidx < (int)n_scenes && scene_last_ev[sidx] < ev_end) ++sidx;
+    return sidx;
+  };
+  bool mix_desc_uploaded = false;
+  SceneDev* d_scenes = (SceneDev*)(dbase + mix_off_scenes);
+  AmbDev* d_ambs = (AmbDev*)(dbase + mix_off_ambs);
+  MixEv* d_mevs = (MixEv*)(dbase + mix_off_mevs);
+  auto upload_mix_desc = [&](cudaStream_t s_) -> int {
+    memcpy(hbase + mix_off_scenes, h_scenes.data(), h_scenes.size() * sizeof(SceneDev));
+    if (!h_ambs.empty()) memcpy(hbase + mix_off_ambs, h_ambs.data(), h_ambs.size() * sizeof(AmbDev));
+    if (!h_mevs.empty()) memcpy(hbase + mix_off_mevs, h_mevs.data(), h_mevs.size() * sizeof(MixEv));
+    CUDA_TRY(cudaMemcpyAsync(dbase + mix_off_scenes, hbase + mix_off_scenes, desc_total - 256 - mix_off_scenes,
+                             cudaMemcpyHostToDevice, s_));
+    ctx->prof.h2d_bytes += (int64_t)(desc_total - 256 - mix_off_scenes);
+    mix_desc_uploaded = true;
+    return ALR_OK;
+  };
+  auto launch_mix = [&](int s0, int s1) -> int {
+    if (s1 <= s0) return ALR_OK;
+    if (!mix_desc_uploaded) {
+      int rc = upload_mix_desc(st);
+      if (rc) return rc;
+    }
+    const int a0 = h_scenes[s0].amb0;
+    const int a1 = h_scenes[s1 - 1].amb0 + h_scenes[s1 - 1].n_amb;
+    for (int a = a0; a < a1; a += 32768) {
+      const int cnt = std::min(32768, a1 - a);
+      k_amb_partial<<<dim3(kAmbSlices, cnt), 256, 0, st>>>(d_ambs + a, d_ambparts);
+      LAUNCH_CHECK(kCatMix);
+    }
+    if (a1 > a0) {
+      k_amb_final<<<ceil_div((long long)(a1 - a0) * 32, 128), 128, 0, st>>>(d_ambs + a0, a1 - a0, d_ambparts);
+      LAUNCH_CHECK(kCatMix);
+    }
+    long long max_t = 0;
+    for (int sidx = s0; sidx < s1; ++sidx) max_t = std::max(max_t, h_scenes[sidx].T);
+    for (int sidx = s0; sidx < s1; sidx += 32768) {
+      const int cnt = std::min(32768, s1 - sidx);
+      k_mix<<<dim3(ceil_div(max_t, 1024), cnt), 256, 0, st>>>(d_scenes + sidx, d_ambs, d_mevs);
+      LAUNCH_CHECK(kCatMix);
+    }
+    if (host_mode) {
+      int rc = download_after_compute(out_mix.data() + s0, (size_t)(s1 - s0));
+      if (rc) return rc;
+    }
+    scenes_mixed = s1;
+    return ALR_OK;
+  };
+
+  if (host_mode) {
+    // the upload stream must not start before work already queued on the caller's stream (e.g. a previous call)
+    cudaEvent_t ev;
+    int rc = next_sync_event(&ev);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev, st));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_h2d, ev, 0));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
+    if (n_scenes > 0) {
+      rc = upload_mix_desc(ctx->s_h2d);  // every later compute_waits_for_uploads() covers it
+      if (rc) return rc;
+    }
+    if (!chunks[0].empty()) {
+      rc = upload_until(chunks[0][0].ev_end);
+      if (rc) return rc;
+    }
+  }
+
   // ---- stream the chunks: plan into pinned memory, upload, launch; the host plans chunk i+1 while the GPU runs chunk i
   for (int ph = 0; ph < 2; ++ph) {
     const auto& evl = *phase_events[ph];
-    for (const Chunk& ch : chunks[ph]) {
+    for (size_t ci = 0; ci < chunks[ph].size(); ++ci) {
+      const Chunk& ch = chunks[ph][ci];
+
       const auto t_plan0 = std::chrono::steady_clock::now();
       const int ne = ch.ev_end - ch.ev_begin;
       char* hb = hbase + ch.base;
@@ -873,8 +1035,24 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         if (!z.pass && d.N == 0) l_tile[n_tile++] = i;
       }
       host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
-      CUDA_TRY(cudaMemcpyAsync(dbase + ch.base, hb, ch.bytes, cudaMemcpyHostToDevice, st));
+      // Descriptors. In host mode they travel on the UPLOAD stream, right behind this chunk's inputs and ahead of the
+      // next chunk's: a copy on the compute stream would sit behind everything already queued on the H2D copy
+      // engine, which starved the kernels until all uploads had finished (ALR_TRACE timeline, round 1).
+      CUDA_TRY(cudaMemcpyAsync(dbase + ch.base, hb, ch.bytes, cudaMemcpyHostToDevice, host_mode ? ctx->s_h2d : st));
       ctx->prof.h2d_bytes += (int64_t)ch.bytes;
+      if (host_mode) {
+        trace_mark(ctx->s_h2d, "upload done", (int)ci);
+        int rc = compute_waits_for_uploads();  // inputs (uploaded one chunk ahead) + descriptors of this chunk
+        if (rc) return rc;
+        if (ph == 0) {
+          // keep the upload stream one chunk ahead of the kernels: first the ambience of the scenes that become
+          // complete with this chunk (needed right after its kernels), then the inputs of the next chunk
+          rc = upload_ambience_until(scenes_done_after(ch.ev_end));
+          if (rc) return rc;
+          rc = upload_until(ci + 1 < chunks[0].size() ? chunks[0][ci + 1].ev_end : (int)n_events);
+          if (rc) return rc;
+        }
+      }
       char* db = dbase + ch.base;
       EvDev* c_evs = (EvDev*)(db + ch.off_evs);
       const IrDev* c_irs = (const IrDev*)(db + ch.off_irs);
@@ -922,34 +1100,46 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         k_apply_gain<<<dim3(kGainSlices, cnt), 256, 0, st>>>(c_evs + e0, c_gain + e0);
         LAUNCH_CHECK(kCatMix);
       }
+      trace_mark(st, "kernels done", (int)ci);
+      if (host_mode) {  // results of this chunk go home while the next chunk computes
+        int rc;
+        if (ph == 0) {
+          std::vector<OutCopy> list;
+          for (int e = ch.ev_begin; e < ch.ev_end; ++e)
+            if (events_in[e].n_irs != -1) list.push_back(out_spatial[e]);
+          rc = download_after_compute(list.data(), list.size());
+          if (rc) return rc;
+          trace_mark(ctx->s_d2h, "event download done", (int)ci);
+          // scenes whose last event is in this chunk: mix them now so that their download overlaps later uploads
+          const int s1 = scenes_done_after(ch.ev_end);
+          if (s1 > scenes_mixed) {
+            rc = compute_waits_for_uploads();  // their ambience
+            if (rc) return rc;
+            rc = launch_mix(scenes_mixed, s1);
+            trace_mark(st, "mix done", (int)ci);
+            trace_mark(ctx->s_d2h, "mix download done", (int)ci);
+          }
+        } else {
+          std::vector<OutCopy> list;
+          for (int e = ch.ev_begin; e < ch.ev_end; ++e) list.push_back(out_dry[dry_parent[e]]);
+          rc = download_after_compute(list.data(), list.size());
+        }
+        if (rc) return rc;
+      }
     }
   }
-  if (n_scenes > 0) {
-    memcpy(hbase + mix_off_scenes, h_scenes.data(), h_scenes.size() * sizeof(SceneDev));
-    if (!h_ambs.empty()) memcpy(hbase + mix_off_ambs, h_ambs.data(), h_ambs.size() * sizeof(AmbDev));
-    if (!h_mevs.empty()) memcpy(hbase + mix_off_mevs, h_mevs.data(), h_mevs.size() * sizeof(MixEv));
-    CUDA_TRY(cudaMemcpyAsync(dbase + mix_off_scenes, hbase + mix_off_scenes, desc_total - 256 - mix_off_scenes,
-                             cudaMemcpyHostToDevice, st));
-    ctx->prof.h2d_bytes += (int64_t)(desc_total - 256 - mix_off_scenes);
-    SceneDev* d_scenes = (SceneDev*)(dbase + mix_off_scenes);
-    AmbDev* d_ambs = (AmbDev*)(dbase + mix_off_ambs);
-    MixEv* d_mevs = (MixEv*)(dbase + mix_off_mevs);
-    if (!h_ambs.empty()) {
-      for (size_t a0 = 0; a0 < h_ambs.size(); a0 += 32768) {
-        const int cnt = (int)std::min<size_t>(32768, h_ambs.size() - a0);
-        k_amb_partial<<<dim3(kAmbSlices, cnt), 256, 0, st>>>(d_ambs + a0, d_ambparts);
-        LAUNCH_CHECK(kCatMix);
-      }
-      k_amb_final<<<ceil_div((long long)h_ambs.size() * 32, 128), 128, 0, st>>>(d_ambs, (int)h_ambs.size(), d_ambparts);
-      LAUNCH_CHECK(kCatMix);
-    }
-    long long max_t = 0;
-    for (const SceneDev& sd : h_scenes) max_t = std::max(max_t, sd.T);
-    for (int64_t s0 = 0; s0 < n_scenes; s0 += 32768) {
-      const int cnt = (int)std::min<int64_t>(32768, n_scenes - s0);
-      k_mix<<<dim3(ceil_div(max_t, 1024), cnt), 256, 0, st>>>(d_scenes + s0, d_ambs, d_mevs);
-      LAUNCH_CHECK(kCatMix);
-    }
+
+  if (host_mode) {  // whatever is left (scenes without events, ...) before the final mixdown
+    int rc = upload_until((int)n_events);
+    if (rc) return rc;
+    rc = upload_ambience_until((int)n_scenes);
+    if (rc) return rc;
+    rc = compute_waits_for_uploads();
+    if (rc) return rc;
+  }
+  {
+    int rc = launch_mix(scenes_mixed, (int)n_scenes);
+    if (rc) return rc;
   }
   ctx->prof.ms_host_plan = host_plan_ms;
 
@@ -958,12 +1148,24 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     CUDA_TRY(cudaMemcpyAsync(ctx->stage_out.p, d_stats, n_events * sizeof(EvStat), cudaMemcpyDeviceToHost, st));
     ctx->prof.d2h_bytes += (int64_t)(n_events * sizeof(EvStat));
   }
-  for (const OutCopy& c : out_copies) {
-    CUDA_TRY(cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, st));
-    ctx->prof.d2h_bytes += (int64_t)c.bytes;
+  if (host_mode) {
+    cudaEvent_t ev;  // the caller's stream finishes only when every download has finished
+    int rc = next_sync_event(&ev);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev, ctx->s_d2h));
+    CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));
   }
   CUDA_TRY(cudaEventRecord(ctx->ev_t1, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  if (trace) {
+    for (auto& m : trace_marks) {
+      float t = 0.f;
+      cudaEventSynchronize(m.ev);
+      cudaEventElapsedTime(&t, ctx->ev_t0, m.ev);
+      fprintf(stderr, "[alr trace] %8.3f ms  chunk %2d  %s\n", t, m.chunk, m.what);
+      cudaEventDestroy(m.ev);
+    }
+  }
   float ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
   ctx->prof.ms_total = ms;
