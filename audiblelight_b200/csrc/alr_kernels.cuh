@@ -421,6 +421,111 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
         if (c < nc) yspec[(ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin] = acc[s][c];
 }
 
+// k_cmac_static: the same contraction for STATIC events (one IR, every source block active), where it is a plain
+// block-FIR  Y[b,c] = sum_k X[b-k] * H[k,c]  and completely regular: all kG outputs of the run are live in every
+// partition step, so there are no per-IR headers, iterators or validity branches. Static events are 40 % of the
+// multiply-accumulates and 72 % of the CTAs of the benchmark workload (and the common case in DCASE-style scenes).
+// One CTA per (event, run of 8 output blocks, 4 capsules, 256 bins), a thread owns one bin:
+//  * source window W[s] = X[b0 + s - k] in registers; the partition loop is unrolled 8x so that the window slides
+//    by register RENAMING (W[(s - r) & 7]), one new row per step, requested one step ahead;
+//  * H[k, c0..c0+3] double-buffered by name (hA / hB), requested one step ahead (static-event H is L2 resident:
+//    96 rows per event shared by all of its CTAs);
+//  * rows outside [0, xnb) are zeros (start of the signal / beyond its end), so the 128 FFMA of a step are
+//    unconditional: ~145 instructions per step instead of ~290 in the generic kernel.
+// Tile per thread: 1 bin x 4 capsules x 8 blocks at 2 CTAs/SM measured best (3.78 ms per benchmark step); 2 capsules
+// (77 registers, 3 CTAs/SM) 4.19 ms, 1 capsule (4 CTAs/SM) 4.49 ms: the extra loads per FFMA outweigh the occupancy;
+// 1 CTA/SM 6.14 ms, i.e. the kernel is latency-bound (profiles/r01_cmac_variants.txt).
+#ifndef ALR_STATIC_CH
+#define ALR_STATIC_CH 4
+#endif
+#ifndef ALR_STATIC_OCC
+#define ALR_STATIC_OCC 2
+#endif
+constexpr int kStaticCh = ALR_STATIC_CH;  // capsules per thread in k_cmac_static
+__global__ void __launch_bounds__(kCtaThreads, ALR_STATIC_OCC)
+k_cmac_static(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const IrDev* __restrict__ irs,
+              const float2* __restrict__ xspec, const float2* __restrict__ hspec, float2* __restrict__ yspec) {
+  const int e = find_segment(prefix, n_ev, blockIdx.x);
+  const EvDev& ev = evs[e];
+  int local = blockIdx.x - __ldg(prefix + e);
+  const int br = local % kBinCtas;
+  local /= kBinCtas;
+  const int ncg = (ev.C + kStaticCh - 1) / kStaticCh;
+  const int cg = local % ncg;
+  const int run = local / ncg;
+  const int c0 = cg * kStaticCh;
+  const int nc = min(kStaticCh, ev.C - c0);
+  const int b0 = run * kG;
+  const int nb = min(kG, ev.B_valid - b0);
+  const int bin = br * kCtaThreads + threadIdx.x;
+  const int K = ev.K, C = ev.C;
+  const int xnb = irs[ev.ir0].xnb;
+  const long long kstride = (long long)C * kP;
+  const float2* __restrict__ xbase = xspec + ev.xslot0 * kP + bin;
+  const float2* __restrict__ hbase = hspec + (ev.hslot0 + c0) * kP + bin;
+  const float2 zero = make_float2(0.f, 0.f);
+  auto load_x = [&](int j) -> float2 { return (j >= 0 && j < xnb) ? __ldg(xbase + (long long)j * kP) : zero; };
+  auto load_h = [&](int k, float2 (&h)[kStaticCh]) {
+    if (k < K) {
+#pragma unroll
+      for (int c = 0; c < kStaticCh; ++c) h[c] = (c < nc) ? __ldg(hbase + k * kstride + (long long)c * kP) : zero;
+    }
+  };
+  float2 acc[kG][kStaticCh];
+#pragma unroll
+  for (int s = 0; s < kG; ++s)
+#pragma unroll
+    for (int c = 0; c < kStaticCh; ++c) acc[s][c] = zero;
+  float2 W[kG], hA[kStaticCh], hB[kStaticCh];
+#pragma unroll
+  for (int s = 0; s < kG; ++s) W[s] = load_x(b0 + s);  // window of partition 0
+#pragma unroll
+  for (int c = 0; c < kStaticCh; ++c) hA[c] = hB[c] = zero;
+  load_h(0, hA);
+  // New source rows are requested TWO steps ahead into two registers that alternate by step parity: the copy into
+  // the window then always reads a value loaded a full step earlier. (Copying a register in the step that loads it
+  // waits for the load: 38 % of all stall samples sat on that single MOV, profiles/r01_cmac_static_v1.txt.)
+  float2 xe = load_x(b0 - 2);  // row of step 2 (even steps)
+  float2 xo = load_x(b0 - 1);  // row of step 1 (odd steps)
+  for (int k0 = 0; k0 < K; k0 += 8) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int k = k0 + r;
+      if (k < K) {
+        // W[(s - r) & 7] == X[b0 + s - k]; the H request for step k + 1 goes out before this step's arithmetic
+        if (r & 1) load_h(k + 1, hA); else load_h(k + 1, hB);
+        const float2 (&h)[kStaticCh] = (r & 1) ? hB : hA;
+#pragma unroll
+        for (int s = 0; s < kG; ++s) {
+          const float2 xv = W[(s - r) & 7];
+#pragma unroll
+          for (int c = 0; c < kStaticCh; ++c) {
+            acc[s][c].x = fmaf(xv.x, h[c].x, acc[s][c].x);
+            acc[s][c].x = fmaf(-xv.y, h[c].y, acc[s][c].x);
+            acc[s][c].y = fmaf(xv.x, h[c].y, acc[s][c].y);
+            acc[s][c].y = fmaf(xv.y, h[c].x, acc[s][c].y);
+          }
+        }
+        // the slot of output 7 of this step becomes output 0 of step k + 1: row b0 - (k + 1), requested during
+        // step k - 1; its register is then free for the row of step k + 3
+        if (r & 1) {  // k + 1 is even
+          W[(7 - r) & 7] = xe;
+          xe = load_x(b0 - k - 3);
+        } else {
+          W[(7 - r) & 7] = xo;
+          xo = load_x(b0 - k - 3);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < kG; ++s)
+    if (s < nb)
+#pragma unroll
+      for (int c = 0; c < kStaticCh; ++c)
+        if (c < nc) yspec[(ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin] = acc[s][c];
+}
+
 // k_ifft_ola: one CTA per (event, group of 4 capsules, run of kRun output blocks); group g handles capsule c0+g.
 // Inverse transform of Y[b]; the real part of element e is sample e of the block, the imaginary part its overlap
 // tail (sample P + e), which the SAME thread adds to block b+1 — the tail never leaves registers. Scale 1/P,

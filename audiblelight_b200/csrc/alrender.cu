@@ -134,7 +134,7 @@ struct EvSize {
   int n_ir = 0;                    // IrDev entries
   int wband = 0;                   // upper bound of cross-fade weight floats
   int n_blk = 0;                   // lrange entries
-  int n_irfft = 0, n_cmac = 0, n_ifft = 0, n_parts = 0;
+  int n_irfft = 0, n_cmac = 0, n_cmac_static = 0, n_ifft = 0, n_parts = 0;
   bool pass = false;
 };
 
@@ -194,7 +194,9 @@ int size_event(const alr_event& u, int idx, EvSize& z) {
   if (z.h > 0x3ffffff0LL || n_cmac > 0x3ffffff0LL || z.xb > 0x3ffffff0LL)
     return fail(ALR_ERR_INVALID, "event %d: too large for 32-bit task indices", idx);
   z.n_irfft = (int)z.h;
-  z.n_cmac = (int)n_cmac;
+  z.n_cmac = moving ? (int)n_cmac : 0;         // generic kernel: moving events
+  const long long n_cmac_s = (long long)ceil_div(z.B_valid, kG) * ((C + kStaticCh - 1) / kStaticCh) * kBinCtas;
+  z.n_cmac_static = moving ? 0 : (int)n_cmac_s;  // regular block-FIR kernel: static events
   z.n_ifft = (int)n_ifft;
   z.n_parts = (int)n_ifft;
   return ALR_OK;
@@ -312,7 +314,7 @@ struct Chunk {
   long long hslots = 0, xslots = 0, yslots = 0;
   int n_ir = 0, n_wband = 0, n_blk = 0;
   size_t off_evs = 0, off_irs = 0, off_wband = 0, off_lrange = 0;
-  size_t off_irfft = 0, off_ir = 0, off_xfft = 0, off_cmac = 0, off_ifft = 0, off_tile = 0, off_dry = 0;
+  size_t off_irfft = 0, off_ir = 0, off_xfft = 0, off_cmac = 0, off_cmacs = 0, off_ifft = 0, off_tile = 0, off_dry = 0;
   size_t bytes = 0;  // blob size
   size_t base = 0;   // offset of the blob in the staging / descriptor buffers
   int part_base = 0, ir_base = 0, gain_base = 0;
@@ -334,6 +336,7 @@ void layout_chunk(Chunk& ch) {
   ch.off_ir = take((size_t)(ne + 1) * sizeof(int));
   ch.off_xfft = take((size_t)(ne + 1) * sizeof(int));
   ch.off_cmac = take((size_t)(ne + 1) * sizeof(int));
+  ch.off_cmacs = take((size_t)(ne + 1) * sizeof(int));
   ch.off_ifft = take((size_t)(ne + 1) * sizeof(int));
   ch.off_tile = take((size_t)ne * sizeof(int));
   ch.off_dry = take((size_t)ne * sizeof(int));
@@ -996,12 +999,13 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       int* p_ir = (int*)(hb + ch.off_ir);
       int* p_xfft = (int*)(hb + ch.off_xfft);
       int* p_cmac = (int*)(hb + ch.off_cmac);
+      int* p_cmacs = (int*)(hb + ch.off_cmacs);
       int* p_ifft = (int*)(hb + ch.off_ifft);
       int* l_tile = (int*)(hb + ch.off_tile);
       int* l_dry = (int*)(hb + ch.off_dry);
       int n_tile = 0, n_dry = 0, ir_off = 0, w_off = 0, blk_off = 0, parts = ch.part_base;
       long long hs = 0, xs = 0, ys = 0;
-      p_irfft[0] = p_ir[0] = p_xfft[0] = p_cmac[0] = p_ifft[0] = 0;
+      p_irfft[0] = p_ir[0] = p_xfft[0] = p_cmac[0] = p_cmacs[0] = p_ifft[0] = 0;
       for (int i = 0; i < ne; ++i) {
         const int ei = ch.ev_begin + i;
         const EvSize& z = sizes[ph][ei];
@@ -1031,6 +1035,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         p_ir[i + 1] = p_ir[i] + z.n_ir;
         p_xfft[i + 1] = p_xfft[i] + x_used;
         p_cmac[i + 1] = p_cmac[i] + z.n_cmac;
+        p_cmacs[i + 1] = p_cmacs[i] + z.n_cmac_static;
         p_ifft[i + 1] = p_ifft[i] + z.n_ifft;
         if (!z.pass && d.N == 0) l_tile[n_tile++] = i;
       }
@@ -1060,7 +1065,8 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       const int2* c_lr = (const int2*)(db + ch.off_lrange);
       float* c_irscale = d_irscale + ch.ir_base;
       float* c_gain = d_gain + ch.gain_base;
-      const int n_irfft = p_irfft[ne], n_xfft = p_xfft[ne], n_cmac = p_cmac[ne], n_ifft = p_ifft[ne], n_irs = p_ir[ne];
+      const int n_irfft = p_irfft[ne], n_xfft = p_xfft[ne], n_cmac = p_cmac[ne], n_cmacs = p_cmacs[ne], n_ifft = p_ifft[ne],
+                n_irs = p_ir[ne];
       if (n_dry > 0) {
         k_dry_window<<<n_dry, 256, 0, st>>>(c_evs, (const int*)(db + ch.off_dry), d_stats);
         LAUNCH_CHECK(kCatOther);
@@ -1082,6 +1088,11 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       if (n_cmac > 0) {
         k_cmac<<<n_cmac, kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_cmac), c_irs, c_lr, d_xspec, d_hspec,
                                               d_yspec);
+        LAUNCH_CHECK(kCatCmac);
+      }
+      if (n_cmacs > 0) {
+        k_cmac_static<<<n_cmacs, kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_cmacs), c_irs, d_xspec, d_hspec,
+                                                      d_yspec);
         LAUNCH_CHECK(kCatCmac);
       }
       if (n_ifft > 0) {
