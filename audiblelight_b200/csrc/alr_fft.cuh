@@ -1,9 +1,11 @@
 // alr_fft.cuh — shared-memory Stockham FFT core (sm_100a), used by every spectral kernel of the renderer.
 //
 // A real block of 2P samples (P signal + P zero padding) is transformed with the negacyclic fold+twist map
-// (see below) and ONE P = 1024 point complex FFT done by a group of 64 threads: Stockham autosort passes of radix
-// 16, 16 and 4, butterflies in registers, two exchanges through shared memory.  This replaces scipy's pocketfft
-// calls of the reference (scipy.fft.rfft/irfft, synthesize.py:138,267; scipy.signal.fftconvolve, :103,490).
+// (see below) and ONE P-point complex FFT done by a group of P/16 threads (16 elements each): Stockham autosort
+// passes of radix 16, 16 and P/256, butterflies in registers, two exchanges through shared memory.  This replaces
+// scipy's pocketfft calls of the reference (scipy.fft.rfft/irfft, synthesize.py:138,267; scipy.signal.fftconvolve,
+// :103,490).  P is a compile-time choice (-DALR_P=1024|2048|4096); 2048 measured best on the benchmark workload
+// (26.5 / 24.5 / 24.9 ms per step: larger partitions trade multiply-accumulates for FFT work, profiles/r01_partition_sweep.txt).
 //
 // Shared-memory layout: float2 elements, one pad element per 16 (index i -> i + i/16).  With 64-bit accesses the
 // hardware serves a warp as two half-warps of 16 lanes x 8 B; with this padding the stride-16 scatter of pass A
@@ -14,16 +16,22 @@
 // Twiddles: only 5 table loads per thread and transform (w^1, w^2, w^4, w^8 of pass B and w_t of pass C); the rest
 // are products of at most three exact table values, so the rounding error stays ~3 ulp.
 //
-// A block spectrum is P ordinary complex values (8 KB).
+// A block spectrum is P ordinary complex values (8 bytes each).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace alr {
 
-constexpr int kP = 1024;          // partition length in samples == complex FFT size
-constexpr int kGroup = 64;        // threads per FFT
-constexpr int kGroupsPerCta = 4;  // FFTs in flight per CTA
+#ifndef ALR_P
+#define ALR_P 2048
+#endif
+constexpr int kP = ALR_P;                    // partition length in samples == complex FFT size (1024, 2048 or 4096)
+static_assert(kP == 1024 || kP == 2048 || kP == 4096, "partition must be 1024, 2048 or 4096");
+constexpr int kGroup = kP / 16;              // threads per FFT (each holds 16 elements): 64, 128 or 256
+constexpr int kGroupsPerCta = 256 / kGroup;  // FFTs in flight per CTA: 4, 2 or 1
+constexpr int kR3 = kP / 256;                // radix of the last pass (16 * 16 * kR3 == kP): 4, 8 or 16
+constexpr int kM3 = 16 / kR3;                // last-pass butterflies per thread: 4, 2 or 1
 constexpr int kPad = kP + kP / 16;
 
 struct FftSmem {
@@ -39,9 +47,9 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
-// barrier over one 64-thread FFT group (named barriers 1..4; 0 stays __syncthreads)
+// barrier over one FFT group of kGroup threads (named barriers 1..4; 0 stays __syncthreads)
 __device__ __forceinline__ void group_sync(int bar) {
-  asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(kGroup) : "memory");
 }
 
 // 4-point DFT, natural order in and out. Forward: exp(-i..); INV: exp(+i..)
@@ -87,18 +95,43 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
 }
 __device__ __forceinline__ constexpr int perm16(int k) { return 4 * (k & 3) + (k >> 2); }
 
-// P-point complex FFT by one 64-thread group.
-//   in : v[r] = element (t + 64 r), r = 0..15                         (t = thread index in the group)
-//   out: o[m][k] = spectrum element (t + 64 m) + 256 k, m,k = 0..3     (natural order, un-normalised)
+// 8-point DFT as 4x2 (n = 2*n1 + n2, k = k1 + 4*k2). Output X[k] ends up in v[2*(k&3) + (k>>2)].
+template <bool INV>
+__device__ __forceinline__ void dft8(float2 (&v)[8]) {
+  dft4<INV>(v[0], v[2], v[4], v[6]);
+  dft4<INV>(v[1], v[3], v[5], v[7]);
+  // v[2*k1 + 1] *= W8^k1
+  const float h = 0.70710678118654752f;
+  {
+    float2 a = v[3];  // W8^1 = (h, -h) forward, (h, +h) inverse
+    v[3] = INV ? make_float2(h * (a.x - a.y), h * (a.x + a.y)) : make_float2(h * (a.x + a.y), h * (a.y - a.x));
+    a = v[5];         // W8^2 = -i forward, +i inverse
+    v[5] = INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+    a = v[7];         // W8^3 = (-h, -h) forward, (-h, +h) inverse
+    v[7] = INV ? make_float2(-h * (a.x + a.y), h * (a.x - a.y)) : make_float2(h * (a.y - a.x), -h * (a.x + a.y));
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+    const float2 a = v[2 * k1], b = v[2 * k1 + 1];
+    v[2 * k1] = cadd(a, b);
+    v[2 * k1 + 1] = csub(a, b);
+  }
+}
+__device__ __forceinline__ constexpr int perm8(int k) { return 2 * (k & 3) + (k >> 2); }
+
+// P-point complex FFT by one group of kGroup = P/16 threads; Stockham autosort, radix 16 x 16 x kR3.
+//   in : v[r] = element (t + kGroup r), r = 0..15                              (t = thread index in the group)
+//   out: o[m][k] = spectrum element (t + kGroup m) + 256 k, m < kM3, k < kR3    (natural order, un-normalised)
 // tw[m] = exp(-2*pi*i*m/P), m < P.  The caller must have a group_sync between any earlier use of `s` by other
-// threads and this call; on return the group may still be reading `s` (pass C gather), so the caller needs a
+// threads and this call; on return the group may still be reading `s` (last-pass gather), so the caller needs a
 // group_sync before the next transform scatters into `s`.
 template <bool INV>
 __device__ __forceinline__ void fft_core(float2 (&v)[16], FftSmem& s, const float2* __restrict__ tw, int t, int bar,
-                                         float2 (&o)[4][4]) {
+                                         float2 (&o)[kM3][kR3]) {
   // twiddle seeds: issue the table loads first so that their latency hides behind pass A
   const int tq = t & 15;
-  float2 w1 = __ldg(tw + 4 * tq), w2 = __ldg(tw + 8 * tq), w4 = __ldg(tw + 16 * tq), w8 = __ldg(tw + 32 * tq);
+  constexpr int kB = kP / 256;  // pass-B twiddle exp(-2 pi i tq r / 256) = tw[tq * r * kB]
+  float2 w1 = __ldg(tw + kB * tq), w2 = __ldg(tw + 2 * kB * tq), w4 = __ldg(tw + 4 * kB * tq), w8 = __ldg(tw + 8 * kB * tq);
   float2 wt = __ldg(tw + t);
   if (INV) {
     w1.y = -w1.y; w2.y = -w2.y; w4.y = -w4.y; w8.y = -w8.y; wt.y = -wt.y;
@@ -109,7 +142,7 @@ __device__ __forceinline__ void fft_core(float2 (&v)[16], FftSmem& s, const floa
   for (int k = 0; k < 16; ++k) s.d[padi(16 * t + k)] = v[perm16(k)];
   group_sync(bar);
 #pragma unroll
-  for (int r = 0; r < 16; ++r) v[r] = s.d[padi(t + 64 * r)];
+  for (int r = 0; r < 16; ++r) v[r] = s.d[padi(t + kGroup * r)];
   group_sync(bar);
   // ---- pass B: radix 16, Ns = 16; twiddle exp(-2 pi i (t%16) r / 256) = w1^r, built from w1, w2, w4, w8
   {
@@ -127,16 +160,16 @@ __device__ __forceinline__ void fft_core(float2 (&v)[16], FftSmem& s, const floa
 #pragma unroll
   for (int k = 0; k < 16; ++k) s.d[padi(base + 16 * k)] = v[perm16(k)];
   group_sync(bar);
-  // ---- pass C: radix 4, Ns = 256; butterfly j = t + 64 m; twiddle exp(-2 pi i j r / 1024) = (wt * c_m)^r,
-  //      c_m = exp(-i pi m / 8)
+  // ---- pass C: radix kR3, Ns = 256; butterfly j = t + kGroup m; twiddle exp(-2 pi i j r / P) = (wt * c_m)^r,
+  //      c_m = exp(-2 pi i kGroup m / P) = exp(-i pi m / 8)
 #pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    const int j = t + 64 * m;
+  for (int m = 0; m < kM3; ++m) {
+    const int j = t + kGroup * m;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) o[m][r] = s.d[padi(j + 256 * r)];
+    for (int r = 0; r < kR3; ++r) o[m][r] = s.d[padi(j + 256 * r)];
   }
 #pragma unroll
-  for (int m = 0; m < 4; ++m) {
+  for (int m = 0; m < kM3; ++m) {
     const float cr[4] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
     const float ci[4] = {0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
     const float2 cm = make_float2(cr[m], INV ? ci[m] : -ci[m]);
@@ -146,11 +179,41 @@ __device__ __forceinline__ void fft_core(float2 (&v)[16], FftSmem& s, const floa
     o[m][1] = cmul(o[m][1], u1);
     o[m][2] = cmul(o[m][2], u2);
     o[m][3] = cmul(o[m][3], u3);
-    dft4<INV>(o[m][0], o[m][1], o[m][2], o[m][3]);
+    if constexpr (kR3 == 16) {
+      const float2 u4 = cmul(u2, u2), u8 = cmul(u4, u4);
+      const float2 u5 = cmul(u4, u1), u6 = cmul(u4, u2), u7 = cmul(u4, u3);
+      o[m][4] = cmul(o[m][4], u4);   o[m][5] = cmul(o[m][5], u5);   o[m][6] = cmul(o[m][6], u6);
+      o[m][7] = cmul(o[m][7], u7);   o[m][8] = cmul(o[m][8], u8);   o[m][9] = cmul(o[m][9], cmul(u8, u1));
+      o[m][10] = cmul(o[m][10], cmul(u8, u2)); o[m][11] = cmul(o[m][11], cmul(u8, u3));
+      o[m][12] = cmul(o[m][12], cmul(u8, u4)); o[m][13] = cmul(o[m][13], cmul(u8, u5));
+      o[m][14] = cmul(o[m][14], cmul(u8, u6)); o[m][15] = cmul(o[m][15], cmul(u8, u7));
+      dft16<INV>(o[m]);
+      float2 tmp[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tmp[k] = o[m][perm16(k)];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) o[m][k] = tmp[k];
+    } else if constexpr (kR3 == 8) {
+      const float2 u4 = cmul(u2, u2);
+      o[m][4] = cmul(o[m][4], u4);
+      o[m][5] = cmul(o[m][5], cmul(u4, u1));
+      o[m][6] = cmul(o[m][6], cmul(u4, u2));
+      o[m][7] = cmul(o[m][7], cmul(u4, u3));
+      dft8<INV>(o[m]);
+      // natural order: X[k] sits in slot perm8(k)
+      float2 tmp[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tmp[k] = o[m][perm8(k)];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[m][k] = tmp[k];
+    } else {
+      dft4<INV>(o[m][0], o[m][1], o[m][2], o[m][3]);
+    }
   }
 }
 
-// exp(+i*pi*64*r/(2P)) = exp(i*pi*r/32): the r-dependent factor of the twist zeta^(t+64r), compile-time after unrolling
+// exp(+i*pi*kGroup*r/(2P)) = exp(i*pi*r/32): the r-dependent factor of the twist zeta^(t + kGroup r) (kGroup = P/16),
+// compile-time after unrolling
 __device__ __forceinline__ float2 zeta_step(int r) {
   constexpr float c[16] = {1.0f,          0.99518472667f, 0.98078528040f, 0.95694033573f, 0.92387953251f, 0.88192126435f,
                            0.83146961230f, 0.77301045336f, 0.70710678119f, 0.63439328416f, 0.55557023302f, 0.47139673683f,
@@ -169,7 +232,7 @@ __device__ __forceinline__ float2 zeta_step(int r) {
 // DC/Nyquist bin, no real-FFT untangle pass), and after the inverse the first half of the block is the real part and
 // the overlap tail the imaginary part of the SAME element.
 //
-// Forward: the caller passes the real samples a[t + 64 r] in a[r] (second half implicitly zero); zt = zeta^t.
+// Forward: the caller passes the real samples a[t + kGroup r] in a[r] (second half implicitly zero); zt = zeta^t.
 __device__ __forceinline__ void fwd_block_to_global(const float (&a)[16], float2 zt, FftSmem& s,
                                                     const float2* __restrict__ tw, int t, int bar,
                                                     float2* __restrict__ spec) {
@@ -179,30 +242,30 @@ __device__ __forceinline__ void fwd_block_to_global(const float (&a)[16], float2
     const float2 z = (r == 0) ? zt : cmul(zt, zeta_step(r));
     v[r] = make_float2(a[r] * z.x, a[r] * z.y);
   }
-  float2 o[4][4];
+  float2 o[kM3][kR3];
   fft_core<false>(v, s, tw, t, bar, o);
 #pragma unroll
-  for (int m = 0; m < 4; ++m)
+  for (int m = 0; m < kM3; ++m)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) spec[t + 64 * m + 256 * k] = o[m][k];
+    for (int k = 0; k < kR3; ++k) spec[t + kGroup * m + 256 * k] = o[m][k];
   group_sync(bar);  // pass-C gathers done before the next transform's scatter
 }
 
-// Inverse: spectrum (global) -> o[m][k] = un-normalised z[e] * conj(zeta^e), e = t + 64 m + 256 k:
+// Inverse: spectrum (global) -> o[m][k] = un-normalised z[e] * conj(zeta^e), e = t + kGroup m + 256 k:
 // real part = block sample e (first half), imaginary part = block sample P + e (overlap tail). Scale by 1/P.
 __device__ __forceinline__ void inv_block_from_global(const float2* __restrict__ spec, float2 zt, FftSmem& s,
                                                       const float2* __restrict__ tw, int t, int bar,
-                                                      float2 (&o)[4][4]) {
+                                                      float2 (&o)[kM3][kR3]) {
   float2 v[16];
 #pragma unroll
-  for (int r = 0; r < 16; ++r) v[r] = spec[t + 64 * r];
+  for (int r = 0; r < 16; ++r) v[r] = spec[t + kGroup * r];
   fft_core<true>(v, s, tw, t, bar, o);
   const float2 ztc = cconj(zt);
 #pragma unroll
-  for (int m = 0; m < 4; ++m)
+  for (int m = 0; m < kM3; ++m)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = m + 4 * k;  // e = t + 64 r
+    for (int k = 0; k < kR3; ++k) {
+      const int r = m + (256 / kGroup) * k;  // e = t + kGroup r
       const float2 z = (r == 0) ? ztc : cmul(ztc, cconj(zeta_step(r)));
       o[m][k] = cmul(o[m][k], z);
     }

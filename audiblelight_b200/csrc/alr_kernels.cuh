@@ -16,7 +16,8 @@
 namespace alr {
 
 constexpr int kCtaThreads = kGroup * kGroupsPerCta;  // 256
-constexpr int kChanGroup = 4;                        // channels per CMAC / IFFT CTA
+constexpr int kChanGroup = 4;                        // capsules per CMAC thread / CTA
+constexpr int kIfftCh = kGroupsPerCta;               // capsules per IFFT CTA (one FFT group each)
 constexpr int kRun = 4;                              // consecutive output blocks per IFFT CTA (tail kept in registers)
 constexpr int kBinCtas = kP / kCtaThreads;           // CMAC CTAs per spectrum (each thread owns one bin)
 
@@ -115,8 +116,8 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
          const float2* __restrict__ tw, const float2* __restrict__ zeta, float2* __restrict__ hspec,
          float* __restrict__ hen) {
   __shared__ FftSmem sm[kGroupsPerCta];
-  __shared__ float s_red[kGroupsPerCta][2];
-  const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
+  __shared__ float s_red[kGroupsPerCta][kGroup / 32];
+  const int g = threadIdx.x / kGroup, t = threadIdx.x % kGroup, bar = 1 + g;
   const int task = blockIdx.x * kGroupsPerCta + g;
   if (task >= n_tasks) return;  // whole group leaves together
   const int e = find_segment(prefix, n_ev, task);
@@ -134,7 +135,7 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
   float en = 0.f;
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
-    const int n = t0 + t + 64 * r;
+    const int n = t0 + t + kGroup * r;
     a[r] = (n >= lo && n < hi) ? __ldg(src + n) : 0.f;
     en = fmaf(a[r], a[r], en);
   }
@@ -142,7 +143,12 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
   en = warp_sum(en);
   if ((t & 31) == 0) s_red[g][t >> 5] = en;
   fwd_block_to_global(a, zt, sm[g], tw, t, bar, hspec + slot * kP);  // contains group barriers
-  if (t == 0) hen[slot] = s_red[g][0] + s_red[g][1];
+  if (t == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kGroup / 32; ++w) tot += s_red[g][w];
+    hen[slot] = tot;
+  }
 }
 
 // k_ir_scale: a_l = 1 / mean_c( sqrt(sum_t h_{l,c}^2) + tiny )  (normalize_irs on the (N, C, Lh) view), times 512
@@ -185,7 +191,7 @@ k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix,
         const float2* __restrict__ tw, const float2* __restrict__ zeta, const float* __restrict__ win,
         float2* __restrict__ xspec) {
   __shared__ FftSmem sm[kGroupsPerCta];
-  const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
+  const int g = threadIdx.x / kGroup, t = threadIdx.x % kGroup, bar = 1 + g;
   const int task = blockIdx.x * kGroupsPerCta + g;
   if (task >= n_tasks) return;
   const int e = find_segment(prefix, n_ev, task);
@@ -207,22 +213,24 @@ k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix,
   const float sc = irscale[ev.ir0 + l];
   const float* __restrict__ x = ev.x;
   const float2 zt = __ldg(zeta + t);
-  float s_even = 0.f, s_odd = 0.f;  // sin^2(pi p / 256) for p = t and p = t + 64
+  // sin^2(pi p / 256) for the in-frame positions of this thread's samples: offset t + kGroup r inside the block, i.e.
+  // p = t (+ 64 for odd r when kGroup == 64)
+  float s_even = 0.f, s_odd = 0.f;
   if (ev.moving) {
-    s_even = __ldg(win + t);
-    s_odd = __ldg(win + t + 64);
+    s_even = __ldg(win + (t & 127));
+    s_odd = __ldg(win + ((t + 64) & 127));
   }
   float a[16];
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
-    const int n = t0 + t + 64 * r;
+    const int n = t0 + t + kGroup * r;
     float v = (n < ev.xlimit) ? __ldg(x + n) : 0.f;
     float gw = sc;
     if (ev.moving) {
-      const int q = (t0 >> 7) + (r >> 1) - ir.jmin;  // STFT frame of sample n (uniform over the group)
+      const int q = (t0 >> 7) + ((t + kGroup * r) >> 7) - ir.jmin;  // STFT frame of sample n
       const float w0 = (q >= 0 && q < ir.nrows) ? __ldg(wband + ir.woff + q) : 0.f;
       const float w1 = (q + 1 >= 0 && q + 1 < ir.nrows) ? __ldg(wband + ir.woff + q + 1) : 0.f;
-      gw = sc * fmaf(w1 - w0, (r & 1) ? s_odd : s_even, w0);  // w0 (1 - s) + w1 s
+      gw = sc * fmaf(w1 - w0, (kGroup == 64 && (r & 1)) ? s_odd : s_even, w0);  // w0 (1 - s) + w1 s
     }
     a[r] = v * gw;
   }
@@ -536,42 +544,42 @@ k_ifft_ola(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ pref
            int part_base) {
   __shared__ FftSmem sm[kGroupsPerCta];
   __shared__ float s_max[kCtaThreads / 32], s_sum[kCtaThreads / 32];
-  const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
+  const int g = threadIdx.x / kGroup, t = threadIdx.x % kGroup, bar = 1 + g;
   const int e = find_segment(prefix, n_ev, blockIdx.x);
   const EvDev& ev = evs[e];
   int local = blockIdx.x - __ldg(prefix + e);
   const int nruns = (ev.B_out + kRun - 1) / kRun;
   const int run = local % nruns;
   const int cg = local / nruns;
-  const int c = cg * kChanGroup + g;
+  const int c = cg * kIfftCh + g;
   float vmax = 0.f, vsum = 0.f;
   if (c < ev.C) {
     const float inv = 1.0f / kP;
     const float2 zt = __ldg(zeta + t);
     float* __restrict__ y = ev.y + (long long)c * ev.n_out;
-    float tail[4][4];
+    float tail[kM3][kR3];
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+    for (int m = 0; m < kM3; ++m)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) tail[m][k] = 0.f;
+      for (int k = 0; k < kR3; ++k) tail[m][k] = 0.f;
     const int b0 = run * kRun;
     const int b1 = min(b0 + kRun, ev.B_out);
     for (int b = max(b0 - 1, 0); b < b1; ++b) {
-      float2 o[4][4];
+      float2 o[kM3][kR3];
       if (b < ev.B_valid) {
         inv_block_from_global(yspec + (ev.yslot0 + (long long)b * ev.C + c) * kP, zt, sm[g], tw, t, bar, o);
       } else {
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+        for (int m = 0; m < kM3; ++m)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) o[m][k] = make_float2(0.f, 0.f);
+          for (int k = 0; k < kR3; ++k) o[m][k] = make_float2(0.f, 0.f);
       }
       if (b >= b0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < kR3; ++k)
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int n = b * kP + t + 64 * m + 256 * k;
+          for (int m = 0; m < kM3; ++m) {
+            const int n = b * kP + t + kGroup * m + 256 * k;
             float a = fmaf(o[m][k].x, inv, tail[m][k]);
             if (n >= ev.n_valid) a = 0.f;
             if (n < ev.n_out) y[n] = a;
@@ -580,9 +588,9 @@ k_ifft_ola(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ pref
           }
       }
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
+      for (int m = 0; m < kM3; ++m)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tail[m][k] = o[m][k].y * inv;
+        for (int k = 0; k < kR3; ++k) tail[m][k] = o[m][k].y * inv;
     }
   }
   vmax = warp_max(vmax);
@@ -827,14 +835,14 @@ __global__ void __launch_bounds__(kCtaThreads)
 k_debug_rfft(const float* __restrict__ in, long long n_blocks, long long in_stride, int n_valid,
              const float2* __restrict__ tw, const float2* __restrict__ zeta, float2* __restrict__ spec) {
   __shared__ FftSmem sm[kGroupsPerCta];
-  const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
+  const int g = threadIdx.x / kGroup, t = threadIdx.x % kGroup, bar = 1 + g;
   const long long blk = (long long)blockIdx.x * kGroupsPerCta + g;
   if (blk >= n_blocks) return;
   const float* src = in + blk * in_stride;
   float a[16];
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
-    const int n = t + 64 * r;
+    const int n = t + kGroup * r;
     a[r] = n < n_valid ? src[n] : 0.f;
   }
   fwd_block_to_global(a, __ldg(zeta + t), sm[g], tw, t, bar, spec + blk * kP);
@@ -844,18 +852,18 @@ __global__ void __launch_bounds__(kCtaThreads)
 k_debug_irfft(const float2* __restrict__ spec, long long n_blocks, const float2* __restrict__ tw,
               const float2* __restrict__ zeta, float* __restrict__ out) {
   __shared__ FftSmem sm[kGroupsPerCta];
-  const int g = threadIdx.x >> 6, t = threadIdx.x & 63, bar = 1 + g;
+  const int g = threadIdx.x / kGroup, t = threadIdx.x % kGroup, bar = 1 + g;
   const long long blk = (long long)blockIdx.x * kGroupsPerCta + g;
   if (blk >= n_blocks) return;
-  float2 o[4][4];
+  float2 o[kM3][kR3];
   inv_block_from_global(spec + blk * kP, __ldg(zeta + t), sm[g], tw, t, bar, o);
   const float inv = 1.0f / kP;
   float* dst = out + blk * 2 * kP;
 #pragma unroll
-  for (int m = 0; m < 4; ++m)
+  for (int m = 0; m < kM3; ++m)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int n = t + 64 * m + 256 * k;
+    for (int k = 0; k < kR3; ++k) {
+      const int n = t + kGroup * m + 256 * k;
       dst[n] = o[m][k].x * inv;
       dst[kP + n] = o[m][k].y * inv;
     }

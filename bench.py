@@ -143,6 +143,14 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def partition_size():
+    try:
+        from audiblelight_b200 import _lib
+        return int(_lib.load().alr_partition_size())
+    except Exception:
+        return None
+
+
 def config_dict(args, world):
     names = {"c5": "configs[4]: batch of one-minute C3-style SELD scenes with moving events (60 s @ 24 kHz, 4 ch, "
                    "1 s RIRs, 6 static + 3 moving events, 10 RIR/s, Gaussian ambience), scene-sharded",
@@ -152,7 +160,7 @@ def config_dict(args, world):
     return {"workload": names[args.workload], "scenes_per_gpu": args.scenes_per_gpu,
             "scenes_total": args.scenes_per_gpu * world, "parallelism": f"scene-sharded x{world}, no collective",
             "cache": "inputs per step (>= 18 GB per GPU at 128 scenes) are far larger than the 126 MB L2",
-            "partition": 1024}
+            "partition": partition_size()}
 
 
 def main():

@@ -36,10 +36,11 @@ def gsc():
 
 
 # ---- FFT core (negacyclic fold+twist transform, alr_fft.cuh) ----------------------------------------------------------
-@pytest.mark.parametrize("n_valid", [1024, 1000, 1, 513])
+@pytest.mark.parametrize("n_valid", [4096, 1000, 1, 513])
 def test_fft_core_forward_inverse(rnd, n_valid):
     import torch
-    P = 1024
+    P = rnd._lib.alr_partition_size()
+    n_valid = min(n_valid, P)
     rng = np.random.default_rng(n_valid)
     x = rng.standard_normal((37, n_valid)).astype(np.float32)
     spec = rnd.debug_rfft(torch.from_numpy(x).cuda())
@@ -57,8 +58,9 @@ def test_fft_core_block_convolution(rnd):
     """Pointwise product of two block spectra == linear convolution of the two P-sample blocks (2P-1 samples)."""
     import torch
     rng = np.random.default_rng(3)
-    a = rng.standard_normal((5, 1024)).astype(np.float32)
-    b = rng.standard_normal((5, 1024)).astype(np.float32)
+    P = rnd._lib.alr_partition_size()
+    a = rng.standard_normal((5, P)).astype(np.float32)
+    b = rng.standard_normal((5, P)).astype(np.float32)
     A = rnd.debug_rfft(torch.from_numpy(a).cuda())
     B = rnd.debug_rfft(torch.from_numpy(b).cuda())
     Ac, Bc = torch.view_as_complex(A.contiguous()), torch.view_as_complex(B.contiguous())
@@ -66,7 +68,7 @@ def test_fft_core_block_convolution(rnd):
     y = rnd.debug_irfft(Y).cpu().numpy()
     for i in range(5):
         ref = np.convolve(a[i].astype(np.float64), b[i].astype(np.float64))
-        assert np.abs(y[i, :2047] - ref).max() < 3e-6 * np.abs(ref).max()
+        assert np.abs(y[i, :2 * P - 1] - ref).max() < 3e-6 * np.abs(ref).max()
 
 
 # ---- render_event_audio vs the reference's golden output --------------------------------------------------------
