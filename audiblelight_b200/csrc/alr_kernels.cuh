@@ -18,7 +18,7 @@ namespace alr {
 constexpr int kCtaThreads = kGroup * kGroupsPerCta;  // 256
 constexpr int kChanGroup = 4;                        // capsules per CMAC thread / CTA
 constexpr int kIfftCh = kGroupsPerCta;               // capsules per IFFT CTA (one FFT group each)
-constexpr int kRun = 4;                              // consecutive output blocks per IFFT CTA (tail kept in registers)
+constexpr int kRun = 8;                              // consecutive output blocks per IFFT CTA (tail kept in registers)
 constexpr int kBinCtas = kP / kCtaThreads;           // CMAC CTAs per spectrum (each thread owns one bin)
 
 enum { kGainEvent = 0, kGainNone = 1, kGainDry = 2, kGainPass = 3 };  // Pass: already rendered, only mixed

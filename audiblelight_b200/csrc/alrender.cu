@@ -89,7 +89,7 @@ struct HostBuf {  // pinned
   }
 };
 
-enum ProfCat { kCatIrFft = 0, kCatXFft, kCatCmac, kCatIfft, kCatMix, kCatOther, kNumCat };
+enum ProfCat { kCatIrFft = 0, kCatXFft, kCatCmac, kCatCmacStatic, kCatIfft, kCatMix, kCatOther, kNumCat };
 
 }  // namespace
 
@@ -1093,7 +1093,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       if (n_cmacs > 0) {
         k_cmac_static<<<n_cmacs, kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_cmacs), c_irs, d_xspec, d_hspec,
                                                       d_yspec);
-        LAUNCH_CHECK(kCatCmac);
+        LAUNCH_CHECK(kCatCmacStatic);
       }
       if (n_ifft > 0) {
         k_ifft_ola<<<n_ifft, kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_ifft), ctx->d_tw, ctx->d_zeta,
@@ -1191,6 +1191,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     ctx->prof.ms_ir_fft = acc[kCatIrFft];
     ctx->prof.ms_x_fft = acc[kCatXFft];
     ctx->prof.ms_cmac = acc[kCatCmac];
+    ctx->prof.ms_cmac_static = acc[kCatCmacStatic];
     ctx->prof.ms_ifft = acc[kCatIfft];
     ctx->prof.ms_mix = acc[kCatMix];
     ctx->prof.ms_other = acc[kCatOther];

@@ -118,7 +118,8 @@ typedef struct alr_profile {
   double ms_total;          /* whole call on the device, incl. copies in ALR_MEM_HOST mode */
   double ms_ir_fft;         /* RIR partition spectra kernel */
   double ms_x_fft;          /* cross-fade + source block spectra kernel */
-  double ms_cmac;           /* spectral multiply-accumulate kernel */
+  double ms_cmac;           /* spectral multiply-accumulate kernel, moving events (k_cmac) */
+  double ms_cmac_static;    /* spectral multiply-accumulate kernel, static events (k_cmac_static) */
   double ms_ifft;           /* inverse FFT + overlap-add + reductions kernel */
   double ms_mix;            /* gain + mixdown kernels (incl. ambience reduction) */
   double ms_other;
