@@ -21,7 +21,14 @@ class AlrEvent(C.Structure):
         ("dry", C.c_void_p),
         ("spatial", C.c_void_p), ("n_out", C.c_int64),
         ("scene", C.c_int32), ("reserved1", C.c_int32), ("scene_start", C.c_int64), ("scene_end", C.c_int64),
+        ("aug_ops", C.c_void_p), ("n_aug_ops", C.c_int32), ("normalize_audio", C.c_int32), ("audio_out", C.c_void_p),
     ]
+
+
+class AlrAugOp(C.Structure):
+    _fields_ = [("type", C.c_int32), ("fade_in_shape", C.c_int32), ("fade_out_shape", C.c_int32),
+                ("fade_in_samples", C.c_int32), ("fade_out_samples", C.c_int32), ("reserved", C.c_int32),
+                ("p", C.c_double * 6)]
 
 
 class AlrScene(C.Structure):
@@ -85,7 +92,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
-    for which, mirror in enumerate((AlrEvent, AlrScene, AlrEventStats, AlrProfile)):
+    for which, mirror in enumerate((AlrEvent, AlrScene, AlrEventStats, AlrProfile, AlrAugOp)):
         if lib.alr_struct_size(which) != C.sizeof(mirror):
             raise AlrenderError(f"ABI mismatch: {mirror.__name__} is {C.sizeof(mirror)} bytes in Python, "
                                 f"{lib.alr_struct_size(which)} in {path}")

@@ -830,6 +830,194 @@ k_mix(const SceneDev* __restrict__ scenes, const AmbDev* __restrict__ ambs, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// f1: linear event augmentations on the dry audio (audiblelight/augmentation.py, applied by Event.load_audio,
+// event.py:530-536). Every op reads `src` and writes `dst` (ping-pong), so Reverse needs no in-place swap.
+enum { kAugGain = 0, kAugInvert = 1, kAugReverse = 2, kAugFade = 3, kAugBiquad = 4, kAugPreemph = 5, kAugDeemph = 6 };
+constexpr int kIirChunk = 512;  // samples per thread of the chunked IIR scan
+
+struct AugDev {       // one (event, op) application
+  const float* src;
+  float* dst;
+  int L;              // samples
+  int type;
+  int fin_shape, fout_shape, fin, fout;
+  int chunk0;         // first entry of the chunk-state scratch (IIR ops)
+  int nchunks;
+  float p[6];
+};
+
+__device__ __forceinline__ float fade_in_curve(int shape, float f) {
+  // augmentation.py:1494-1508 (f = linspace(0, 1, fade_len)[n])
+  const float pi = 3.14159265358979323846f;
+  switch (shape) {
+    case 1: f = exp2f(f - 1.f) * f; break;                        // exponential
+    case 2: f = log10f(0.1f + f) + 1.f; break;                    // logarithmic
+    case 3: f = sinf(f * pi / 2.f); break;                        // quarter sine
+    case 4: f = sinf(f * pi - pi / 2.f) / 2.f + 0.5f; break;      // half sine
+    default: break;                                               // linear
+  }
+  return fminf(fmaxf(f, 0.f), 1.f);
+}
+__device__ __forceinline__ float fade_out_curve(int shape, float f) {
+  // augmentation.py:1516-1530
+  const float pi = 3.14159265358979323846f;
+  switch (shape) {
+    case 0: f = 1.f - f; break;
+    case 1: f = exp2f(-f) * (1.f - f); break;
+    case 2: f = log10f(1.1f - f) + 1.f; break;
+    case 3: f = sinf(f * pi / 2.f + pi / 2.f); break;
+    case 4: f = sinf(f * pi + pi / 2.f) / 2.f + 0.5f; break;
+    default: break;
+  }
+  return fminf(fmaxf(f, 0.f), 1.f);
+}
+
+// Gain / Invert / Reverse / Fade / Preemphasis (all without recursion). grid = (slices, ops)
+__global__ void k_aug_pointwise(const AugDev* __restrict__ ops) {
+  const AugDev& o = ops[blockIdx.y];
+  const int L = o.L;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < L; n += gridDim.x * blockDim.x) {
+    float v;
+    switch (o.type) {
+      case kAugGain: v = o.p[0] * o.src[n]; break;
+      case kAugInvert: v = -o.src[n]; break;
+      case kAugReverse: v = o.src[L - 1 - n]; break;
+      case kAugFade: {
+        float f = 1.f;
+        if (o.fin > 0 && o.fin_shape != 5 && n < o.fin)
+          f *= fade_in_curve(o.fin_shape, o.fin > 1 ? (float)n / (float)(o.fin - 1) : 0.f);
+        if (o.fout > 0 && o.fout_shape != 5 && n >= L - o.fout) {
+          const int i = n - (L - o.fout);
+          f *= fade_out_curve(o.fout_shape, o.fout > 1 ? (float)i / (float)(o.fout - 1) : 0.f);
+        }
+        v = o.src[n] * f;
+        break;
+      }
+      case kAugPreemph: {
+        // librosa.effects.preemphasis: lfilter([1, -coef], [1], x, zi = 2 x[0] - x[1])  ->  y[0] = x[0] + zi
+        const float c = o.p[0];
+        if (n == 0) v = o.src[0] + (L > 1 ? 2.f * o.src[0] - o.src[1] : o.src[0]);
+        else v = o.src[n] - c * o.src[n - 1];
+        break;
+      }
+      default: v = o.src[n]; break;
+    }
+    o.dst[n] = v;
+  }
+}
+
+// Recursive filters (biquad, de-emphasis) as a chunked scan: with the transposed direct form II state s = (s1, s2)
+//   y = b0 x + s1;  s1' = b1 x - a1 y + s2;  s2' = b2 x - a2 y
+// a chunk maps s_in -> A^Lc s_in + s_zs (A = [[-a1, 1], [-a2, 0]]). Pass 1: zero-state run of every chunk (s_zs);
+// combine: sequential over the chunks of one op in double; pass 2: re-run every chunk from its true s_in.
+__device__ __forceinline__ void iir_coeffs(const AugDev& o, float& b0, float& b1, float& b2, float& a1, float& a2) {
+  if (o.type == kAugDeemph) {  // y[n] = x[n] + coef y[n-1]
+    b0 = 1.f; b1 = 0.f; b2 = 0.f; a1 = -o.p[0]; a2 = 0.f;
+  } else {
+    b0 = o.p[0]; b1 = o.p[1]; b2 = o.p[2]; a1 = o.p[3]; a2 = o.p[4];
+  }
+}
+__global__ void k_iir_pass1(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix, int n_ops, int n_chunks,
+                            float2* __restrict__ zs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  const int oi = find_segment(chunk_prefix, n_ops, c);
+  const AugDev& o = ops[oi];
+  float b0, b1, b2, a1, a2;
+  iir_coeffs(o, b0, b1, b2, a1, a2);
+  const int n0 = (c - chunk_prefix[oi]) * kIirChunk, n1 = min(n0 + kIirChunk, o.L);
+  float s1 = 0.f, s2 = 0.f;
+  for (int n = n0; n < n1; ++n) {
+    const float x = o.src[n];
+    const float y = fmaf(b0, x, s1);
+    s1 = fmaf(b1, x, fmaf(-a1, y, s2));
+    s2 = fmaf(b2, x, -a2 * y);
+  }
+  zs[c] = make_float2(s1, s2);
+}
+__global__ void k_iir_combine(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix, int n_ops,
+                              float2* __restrict__ zs) {
+  const int oi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (oi >= n_ops) return;
+  const AugDev& o = ops[oi];
+  float b0, b1, b2, a1f, a2f;
+  iir_coeffs(o, b0, b1, b2, a1f, a2f);
+  // M = A^kIirChunk by repeated squaring (kIirChunk is a power of two)
+  double m00 = -a1f, m01 = 1.0, m10 = -a2f, m11 = 0.0;
+  for (int q = 1; q < kIirChunk; q <<= 1) {
+    const double n00 = m00 * m00 + m01 * m10, n01 = m00 * m01 + m01 * m11;
+    const double n10 = m10 * m00 + m11 * m10, n11 = m10 * m01 + m11 * m11;
+    m00 = n00; m01 = n01; m10 = n10; m11 = n11;
+  }
+  double s1 = 0.0, s2 = 0.0;  // state entering chunk 0 (pedalboard runs with reset=True; de-emphasis starts from zeros)
+  const int c0 = chunk_prefix[oi], c1 = chunk_prefix[oi + 1];
+  for (int c = c0; c < c1; ++c) {
+    const float2 z = zs[c];
+    zs[c] = make_float2((float)s1, (float)s2);  // replace the zero-state result by the true entry state
+    const double t1 = m00 * s1 + m01 * s2 + z.x, t2 = m10 * s1 + m11 * s2 + z.y;
+    s1 = t1;
+    s2 = t2;
+  }
+}
+__global__ void k_iir_pass2(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix, int n_ops, int n_chunks,
+                            const float2* __restrict__ zs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  const int oi = find_segment(chunk_prefix, n_ops, c);
+  const AugDev& o = ops[oi];
+  float b0, b1, b2, a1, a2;
+  iir_coeffs(o, b0, b1, b2, a1, a2);
+  const int n0 = (c - chunk_prefix[oi]) * kIirChunk, n1 = min(n0 + kIirChunk, o.L);
+  float s1 = zs[c].x, s2 = zs[c].y;
+  // librosa.effects.deemphasis subtracts ((2 - coef) x0 - x1) / (3 - coef) * coef^n afterwards
+  float corr = 0.f, cpow = 1.f;
+  if (o.type == kAugDeemph && o.L > 1) {
+    const float cf = o.p[0];
+    corr = ((2.f - cf) * o.src[0] - o.src[1]) / (3.f - cf);
+    cpow = powf(cf, (float)n0);
+  }
+  for (int n = n0; n < n1; ++n) {
+    const float x = o.src[n];
+    const float y = fmaf(b0, x, s1);
+    s1 = fmaf(b1, x, fmaf(-a1, y, s2));
+    s2 = fmaf(b2, x, -a2 * y);
+    if (o.type == kAugDeemph) {
+      o.dst[n] = y - corr * cpow;
+      cpow *= o.p[0];
+    } else {
+      o.dst[n] = y;
+    }
+  }
+}
+
+// peak normalisation of Event.load_audio: x / max(|x| + tiny)   (event.py:535-536). grid = (slices, events)
+struct NormDev {
+  float* x;
+  int L;
+  int part0;
+};
+__global__ void k_peak_partial(const NormDev* __restrict__ nd, float* __restrict__ partials) {
+  __shared__ float s_max[32];
+  const NormDev& d = nd[blockIdx.y];
+  float m = 0.f;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < d.L; n += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(d.x[n]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_max[w]);
+    partials[d.part0 + blockIdx.x] = m;
+  }
+}
+__global__ void k_peak_scale(const NormDev* __restrict__ nd, const float* __restrict__ partials, int slices) {
+  const NormDev& d = nd[blockIdx.y];
+  float m = 0.f;
+  for (int i = 0; i < slices; ++i) m = fmaxf(m, partials[d.part0 + i]);
+  const float inv = 1.0f / (m + 1.17549435e-38f);  // tiny(float32)
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < d.L; n += gridDim.x * blockDim.x) d.x[n] *= inv;
+}
+
 // ---- unit-test kernels for the FFT core ---------------------------------------------------------------------
 __global__ void __launch_bounds__(kCtaThreads)
 k_debug_rfft(const float* __restrict__ in, long long n_blocks, long long in_stride, int n_valid,

@@ -98,8 +98,8 @@ struct alr_context {
   float2* d_tw = nullptr;    // exp(-2 pi i m / P), m < P
   float2* d_zeta = nullptr;  // exp(+i pi t / 2P), t < 64 (twist seed of thread t)
   float* d_win = nullptr;  // sin^2(pi p / 256), p < 128
-  DevBuf spec, desc, misc, arena;
-  HostBuf stage, stage_out;
+  DevBuf spec, desc, misc, arena, augbuf, augdesc;
+  HostBuf stage, stage_out, stage_aug;
   int64_t ws_limit = (int64_t)2 << 30;
   int profiling = 0;
   alr_profile prof{};
@@ -127,6 +127,16 @@ constexpr int kAmbSlices = 64;
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Blob {  // host-side byte blob with 16-byte aligned sections
+  std::vector<unsigned char> bytes;
+  size_t add(const void* src, size_t n) {
+    size_t off = (bytes.size() + 15) & ~size_t(15);
+    bytes.resize(off + n);
+    if (n) memcpy(bytes.data() + off, src, n);
+    return off;
+  }
+};
 
 struct EvSize {
   int K = 0, n_valid = 0, B_valid = 0, B_out = 0, xlimit = 0;
@@ -432,6 +442,7 @@ int alr_struct_size(int which) {
     case 1: return (int)sizeof(alr_scene);
     case 2: return (int)sizeof(alr_event_stats);
     case 3: return (int)sizeof(alr_profile);
+    case 4: return (int)sizeof(alr_aug_op);
     default: return -1;
   }
 }
@@ -471,8 +482,11 @@ void alr_destroy(alr_context* ctx) {
   ctx->desc.release();
   ctx->misc.release();
   ctx->arena.release();
+  ctx->augbuf.release();
+  ctx->augdesc.release();
   ctx->stage.release();
   ctx->stage_out.release();
+  ctx->stage_aug.release();
   for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
   for (auto ev : ctx->sync_pool) cudaEventDestroy(ev);
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -543,6 +557,8 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     size_t bytes;
     int kind;  // 0 linear, 1 IR block
     int ev;    // event that first needs it (copies are listed in event order); -1: ambience
+    bool is_audio = false;  // dry audio (small): uploaded up front when any event is augmented on the device
+    bool done = false;
   };
   std::vector<OutCopy> out_spatial(mem_space == ALR_MEM_HOST ? n_events : 0), out_dry(mem_space == ALR_MEM_HOST ? n_events : 0);
   std::vector<OutCopy> out_mix;
@@ -574,7 +590,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       if (it == seen.end()) {
         size_t off = reserve(u.n_audio * sizeof(float));
         seen[u.audio] = off;
-        in_copies.push_back({u.audio, off, (size_t)u.n_audio * sizeof(float), 0, (int)i});
+        in_copies.push_back({u.audio, off, (size_t)u.n_audio * sizeof(float), 0, (int)i, true, false});
         off_audio[i] = off;
       } else {
         off_audio[i] = it->second;
@@ -650,6 +666,88 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       for (int a = 0; a < u.n_ambience; ++a) amb_ptrs[s][a] = (const float*)(base + off_amb[s][a]);
       out_mix.push_back({u.mix, base + off_mix[s], (size_t)u.n_channels * u.n_samples * sizeof(float)});
       u.mix = (float*)(base + off_mix[s]);
+    }
+  }
+
+  // ---- f1: device-side augmentation of the dry audio (ping-pong buffers; the event then reads the final buffer) -------
+  constexpr int kAugLevels = 8, kAugSlices = 16;
+  std::vector<AugDev> aug_point[kAugLevels], aug_iir[kAugLevels];
+  std::vector<int> aug_iir_prefix[kAugLevels];
+  std::vector<NormDev> aug_norm;
+  struct AudioOut {
+    void* dst;
+    const void* src;
+    size_t bytes;
+  };
+  std::vector<AudioOut> aug_audio_out;
+  int aug_chunks_total = 0, aug_any = 0;
+  {
+    size_t aug_floats = 0;
+    for (int64_t i = 0; i < n_events; ++i) {
+      const alr_event& u = events_in[i];
+      if (u.n_irs == -1 || (u.n_aug_ops <= 0 && !u.normalize_audio)) continue;
+      if (u.n_aug_ops > kAugLevels) return fail(ALR_ERR_INVALID, "event %d: more than %d augmentations", (int)i, kAugLevels);
+      if (u.n_aug_ops > 0 && !u.aug_ops) return fail(ALR_ERR_INVALID, "event %d: aug_ops is NULL", (int)i);
+      aug_floats += 2 * align_up((size_t)u.n_audio, 64);
+      ++aug_any;
+    }
+    if (aug_any) {
+      int rc = ctx->augbuf.ensure(aug_floats * sizeof(float));
+      if (rc) return rc;
+      float* base = (float*)ctx->augbuf.p;
+      size_t off = 0;
+      for (int l = 0; l < kAugLevels; ++l) aug_iir_prefix[l].push_back(0);
+      for (int64_t i = 0; i < n_events; ++i) {
+        const alr_event& uin = events_in[i];
+        alr_event& u = events[i];
+        if (uin.n_irs == -1 || (uin.n_aug_ops <= 0 && !uin.normalize_audio)) continue;
+        const int L = (int)u.n_audio;
+        float* bufA = base + off;
+        float* bufB = bufA + align_up((size_t)L, 64);
+        off += 2 * align_up((size_t)L, 64);
+        const float* src = u.audio;  // device pointer (already staged in host mode)
+        const int n_ops = std::max(1, uin.n_aug_ops);  // normalise-only events get an identity gain (copy)
+        for (int l = 0; l < n_ops; ++l) {
+          AugDev a;
+          memset(&a, 0, sizeof(a));
+          a.src = src;
+          a.dst = (l & 1) ? bufB : bufA;
+          a.L = L;
+          if (uin.n_aug_ops <= 0) {
+            a.type = kAugGain;
+            a.p[0] = 1.f;
+          } else {
+            const alr_aug_op& op = uin.aug_ops[l];
+            if (op.type < 0 || op.type > kAugDeemph) return fail(ALR_ERR_INVALID, "event %d: bad augmentation type %d", (int)i, op.type);
+            a.type = op.type;
+            a.fin_shape = op.fade_in_shape;
+            a.fout_shape = op.fade_out_shape;
+            a.fin = std::min(std::max(op.fade_in_samples, 0), L);
+            a.fout = std::min(std::max(op.fade_out_samples, 0), L);
+            for (int q = 0; q < 6; ++q) a.p[q] = (float)op.p[q];
+          }
+          if (a.type == kAugBiquad || a.type == kAugDeemph) {
+            a.nchunks = ceil_div(L, kIirChunk);
+            a.chunk0 = aug_chunks_total;
+            aug_chunks_total += a.nchunks;
+            aug_iir[l].push_back(a);
+            aug_iir_prefix[l].push_back(aug_iir_prefix[l].back() + a.nchunks);
+          } else {
+            aug_point[l].push_back(a);
+          }
+          src = a.dst;
+        }
+        float* fin = const_cast<float*>(src);
+        if (uin.normalize_audio) {
+          NormDev nd;
+          nd.x = fin;
+          nd.L = L;
+          nd.part0 = (int)aug_norm.size() * kAugSlices;
+          aug_norm.push_back(nd);
+        }
+        if (uin.audio_out) aug_audio_out.push_back({uin.audio_out, fin, (size_t)L * sizeof(float)});
+        u.audio = fin;
+      }
     }
   }
 
@@ -863,6 +961,10 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     while (in_cursor < in_copies.size()) {
       const InCopy& c = in_copies[in_cursor];
       if (c.ev >= ev_end) break;
+      if (c.done) {
+        ++in_cursor;
+        continue;
+      }
       if (c.kind == 0) {
         CUDA_TRY(cudaMemcpyAsync(arena_base + c.off, c.host, c.bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
       } else {
@@ -979,6 +1081,78 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     if (!chunks[0].empty()) {
       rc = upload_until(chunks[0][0].ev_end);
       if (rc) return rc;
+    }
+  }
+
+  // ---- f1: run the augmentation chains (all events, before the chunk pipeline; the dry audio is ~1 % of the bytes)
+  if (aug_any) {
+    if (host_mode) {  // dry audio first
+      for (InCopy& c : in_copies) {
+        if (!c.is_audio || c.done) continue;
+        CUDA_TRY(cudaMemcpyAsync(arena_base + c.off, c.host, c.bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+        ctx->prof.h2d_bytes += (int64_t)c.bytes;
+        c.done = true;
+      }
+    }
+    // descriptor blob: per level [pointwise ops][iir ops][iir chunk prefix], then the normalisation list
+    Blob ab;
+    size_t off_point[kAugLevels], off_iir[kAugLevels], off_pref[kAugLevels];
+    for (int l = 0; l < kAugLevels; ++l) {
+      off_point[l] = ab.add(aug_point[l].data(), aug_point[l].size() * sizeof(AugDev));
+      off_iir[l] = ab.add(aug_iir[l].data(), aug_iir[l].size() * sizeof(AugDev));
+      off_pref[l] = ab.add(aug_iir_prefix[l].data(), aug_iir_prefix[l].size() * sizeof(int));
+    }
+    const size_t off_norm = ab.add(aug_norm.data(), aug_norm.size() * sizeof(NormDev));
+    const size_t off_zs = align_up(ab.bytes.size(), 256);
+    const size_t off_peaks = align_up(off_zs + (size_t)std::max(aug_chunks_total, 1) * sizeof(float2), 256);
+    const size_t aug_total = off_peaks + std::max<size_t>(aug_norm.size(), 1) * kAugSlices * sizeof(float);
+    {
+      int rc = ctx->augdesc.ensure(aug_total);
+      if (rc) return rc;
+      rc = ctx->stage_aug.ensure(ab.bytes.size() + 16);
+      if (rc) return rc;
+    }
+    memcpy(ctx->stage_aug.p, ab.bytes.data(), ab.bytes.size());
+    char* ad = (char*)ctx->augdesc.p;
+    CUDA_TRY(cudaMemcpyAsync(ad, ctx->stage_aug.p, ab.bytes.size(), cudaMemcpyHostToDevice, host_mode ? ctx->s_h2d : st));
+    ctx->prof.h2d_bytes += (int64_t)ab.bytes.size();
+    if (host_mode) {
+      int rc = compute_waits_for_uploads();
+      if (rc) return rc;
+    }
+    float2* d_zs = (float2*)(ad + off_zs);
+    float* d_peaks = (float*)(ad + off_peaks);
+    for (int l = 0; l < kAugLevels; ++l) {
+      if (!aug_point[l].empty()) {
+        k_aug_pointwise<<<dim3(kAugSlices, (unsigned)aug_point[l].size()), 256, 0, st>>>((const AugDev*)(ad + off_point[l]));
+        LAUNCH_CHECK(kCatOther);
+      }
+      if (!aug_iir[l].empty()) {
+        const int n_ops = (int)aug_iir[l].size(), n_ch = aug_iir_prefix[l].back();
+        const AugDev* dops = (const AugDev*)(ad + off_iir[l]);
+        const int* dpref = (const int*)(ad + off_pref[l]);
+        // the zero-state scratch is indexed by the level-local chunk number
+        k_iir_pass1<<<ceil_div(n_ch, 128), 128, 0, st>>>(dops, dpref, n_ops, n_ch, d_zs);
+        LAUNCH_CHECK(kCatOther);
+        k_iir_combine<<<ceil_div(n_ops, 64), 64, 0, st>>>(dops, dpref, n_ops, d_zs);
+        LAUNCH_CHECK(kCatOther);
+        k_iir_pass2<<<ceil_div(n_ch, 128), 128, 0, st>>>(dops, dpref, n_ops, n_ch, d_zs);
+        LAUNCH_CHECK(kCatOther);
+      }
+    }
+    if (!aug_norm.empty()) {
+      const NormDev* dn = (const NormDev*)(ad + off_norm);
+      for (size_t n0 = 0; n0 < aug_norm.size(); n0 += 32768) {
+        const unsigned cnt = (unsigned)std::min<size_t>(32768, aug_norm.size() - n0);
+        k_peak_partial<<<dim3(kAugSlices, cnt), 256, 0, st>>>(dn + n0, d_peaks);
+        LAUNCH_CHECK(kCatOther);
+        k_peak_scale<<<dim3(kAugSlices, cnt), 256, 0, st>>>(dn + n0, d_peaks, kAugSlices);
+        LAUNCH_CHECK(kCatOther);
+      }
+    }
+    for (const AudioOut& ao : aug_audio_out) {
+      CUDA_TRY(cudaMemcpyAsync(ao.dst, ao.src, ao.bytes, host_mode ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+      if (host_mode) ctx->prof.d2h_bytes += (int64_t)ao.bytes;
     }
   }
 

@@ -13,7 +13,9 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import ALR_GAIN_EVENT, ALR_GAIN_NONE, ALR_MEM_DEVICE, ALR_MEM_HOST, AlrEvent, AlrEventStats, AlrProfile, AlrScene
+from . import augment as _augment
+from ._lib import (ALR_GAIN_EVENT, ALR_GAIN_NONE, ALR_MEM_DEVICE, ALR_MEM_HOST, AlrAugOp, AlrEvent, AlrEventStats,
+                   AlrProfile, AlrScene)
 
 FFT_SIZE, WIN_SIZE, HOP_SIZE = 512, 256, 128  # the only STFT geometry the kernels implement (config.py:9-11)
 
@@ -67,6 +69,10 @@ class EventJob:
     dry_out: object = None                # (Lx+Lh-1,) float32 out
     prerendered: bool = False             # spatial is an input that is only mixed
     stats: Optional[dict] = None
+    # f1: linear augmentations applied to the dry audio on the device before the convolution (audiblelight_b200.augment)
+    aug_ops: Sequence[object] = ()        # list of augment.AugOp, applied in order
+    normalize_audio: bool = False         # then x / max(|x| + tiny) as Event.load_audio(normalize=True)
+    audio_out: object = None              # optional (Lx,) float32 out: the augmented / normalised dry audio
 
 
 @dataclass
@@ -182,6 +188,23 @@ class Renderer:
                     keep.append(fr)
                     a.ir_frames = fr.ctypes.data
                     a.n_frames = int(e.n_frames)
+                if e.aug_ops:
+                    ops = (AlrAugOp * len(e.aug_ops))()
+                    for k, op in enumerate(e.aug_ops):
+                        ops[k].type = int(op.type)
+                        ops[k].fade_in_shape, ops[k].fade_out_shape = int(op.fade_in_shape), int(op.fade_out_shape)
+                        if op.type == _augment.ALR_AUG_FADE:
+                            ops[k].fade_in_samples, ops[k].fade_out_samples = _augment.fade_samples(op, lx)
+                        for q, v in enumerate(op.p):
+                            ops[k].p[q] = float(v)
+                    keep.append(ops)
+                    a.aug_ops = C.cast(ops, C.c_void_p)
+                    a.n_aug_ops = len(e.aug_ops)
+                a.normalize_audio = 1 if e.normalize_audio else 0
+                if (e.aug_ops or e.normalize_audio) and e.audio_out is not None:
+                    if tuple(e.audio_out.shape) != (lx,):
+                        raise ValueError("audio_out must have shape (n_audio,)")
+                    a.audio_out = _ptr(e.audio_out)
                 a.normalize_irs = 1 if e.normalize_irs else 0
                 a.gain_mode = int(e.gain_mode)
                 a.snr = float(e.snr)

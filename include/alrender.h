@@ -51,6 +51,38 @@ enum {
 typedef struct alr_context alr_context;
 
 /*
+ * Linear event augmentations applied to the dry audio BEFORE the convolution ("next" row f1 of the scope table):
+ * the effects of audiblelight/augmentation.py that are linear filters, as Event.load_audio applies them
+ * (event.py:530-532), followed by its peak normalisation (event.py:535-536) when alr_event.normalize_audio is set.
+ * Fade / Invert / Reverse are fully specified by the reference's own numpy code (augmentation.py:1490-1601) and are
+ * pinned by golden vectors; Gain and the IIR filters wrap pedalboard (JUCE) and librosa, which are neither vendored
+ * nor installed offline: their arithmetic here follows the published formulas (host side: audiblelight_b200/
+ * augment.py) and is checked against scipy.signal.lfilter only -> parity UNPINNED for those.
+ */
+enum {
+  ALR_AUG_GAIN = 0,        /* y = p[0] * x                         (Gain, augmentation.py:1105; p[0] = 10^(dB/20)) */
+  ALR_AUG_INVERT = 1,      /* y = -x                               (Invert, :1557) */
+  ALR_AUG_REVERSE = 2,     /* y[n] = x[L-1-n]                      (Reverse, :1583) */
+  ALR_AUG_FADE = 3,        /* y = x * fade_in * fade_out           (Fade, :1403-1554) */
+  ALR_AUG_BIQUAD = 4,      /* y[n] = p0 x[n] + p1 x[n-1] + p2 x[n-2] - p3 y[n-1] - p4 y[n-2], zero initial state
+                              (Low/HighpassFilter :303/:406 first order; Low/HighShelfFilter :348/:449; PeakFilter :643) */
+  ALR_AUG_PREEMPHASIS = 5, /* librosa.effects.preemphasis(coef = p[0])   (:1350) */
+  ALR_AUG_DEEMPHASIS = 6   /* librosa.effects.deemphasis(coef = p[0])    (:1388) */
+};
+enum { ALR_FADE_LINEAR = 0, ALR_FADE_EXPONENTIAL = 1, ALR_FADE_LOGARITHMIC = 2, ALR_FADE_QUARTER_SINE = 3,
+       ALR_FADE_HALF_SINE = 4, ALR_FADE_NONE = 5 };
+
+typedef struct alr_aug_op {
+  int32_t type;             /* ALR_AUG_* */
+  int32_t fade_in_shape;    /* ALR_FADE_* */
+  int32_t fade_out_shape;
+  int32_t fade_in_samples;  /* min(int(round(fade_in_len * sr)), L)  (augmentation.py:1536-1541) */
+  int32_t fade_out_samples;
+  int32_t reserved;
+  double p[6];
+} alr_aug_op;
+
+/*
  * One (event, microphone) render = one call of the reference's render_event_audio (synthesize.py:507).
  * All sample data is float32 (the reference computes in float64; the contract is max-abs error <= 1e-5 of
  * full scale, BASELINE.json north_star).
@@ -91,6 +123,11 @@ typedef struct alr_event {
   int32_t reserved1;
   int64_t scene_start;      /* max(0, round(event.scene_start*sr))                 (:361) */
   int64_t scene_end;        /* min(round(event.scene_end*sr), n_samples); events with end<=start are skipped (:362-369) */
+  /* ---- optional device-side augmentation of the dry audio (f1) ---- */
+  const alr_aug_op* aug_ops; /* HOST array (n_aug_ops), applied in order; NULL = none */
+  int32_t n_aug_ops;
+  int32_t normalize_audio;   /* 1: divide by max(|x| + tiny) afterwards, as Event.load_audio(normalize=True) */
+  float* audio_out;          /* optional out (n_audio): the augmented / normalised dry audio (== event.audio) */
 } alr_event;
 
 /* One (scene, microphone) mixdown = one iteration of the mic loop of generate_scene_audio_from_events (:325-401). */
@@ -133,7 +170,7 @@ typedef struct alr_profile {
 
 int alr_version(void);
 const char* alr_last_error(void);
-/* sizeof() of the ABI structs as compiled: 0 alr_event, 1 alr_scene, 2 alr_event_stats, 3 alr_profile
+/* sizeof() of the ABI structs as compiled: 0 alr_event, 1 alr_scene, 2 alr_event_stats, 3 alr_profile, 4 alr_aug_op
  * (lets a binding verify its mirror of the layout; returns -1 for an unknown id) */
 int alr_struct_size(int which);
 

@@ -118,3 +118,26 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_augment_golden():
+    """Fade / Invert / Reverse of the unmodified reference (augmentation.py:1403-1601) -> tests/golden/augment.npz."""
+    ref_loader.load_reference_synthesize()
+    import audiblelight.augmentation as aug
+    out = {}
+    x = np.random.default_rng(77).standard_normal(6000).astype(np.float32)
+    out["x"] = x
+    fade_cases = [(24000, 0.05, 0.1, "half_sine", "logarithmic"), (24000, 0.0, 0.2, "none", "exponential"),
+                  (16000, 0.125, 0.0, "quarter_sine", "none"), (44100, 0.01, 0.01, "linear", "linear"),
+                  (24000, 1.0, 1.0, "exponential", "quarter_sine"), (24000, 0.1, 0.05, "logarithmic", "half_sine")]
+    out["fade_cases"] = np.array([[c[0], c[1], c[2], aug.Fade.FADE_SHAPES.index(c[3]), aug.Fade.FADE_SHAPES.index(c[4])]
+                                  for c in fade_cases])
+    for i, (sr, fi, fo, si, so) in enumerate(fade_cases):
+        out[f"fade_{i}"] = aug.Fade(sample_rate=sr, fade_in_len=fi, fade_out_len=fo, fade_in_shape=si, fade_out_shape=so)(x)
+    out["invert"] = aug.Invert(24000)(x)
+    out["reverse"] = aug.Reverse(24000)(x)
+    np.savez_compressed(os.path.join(HERE, "augment.npz"), **out)
+
+
+if __name__ == "__main__":
+    make_augment_golden()

@@ -1,0 +1,157 @@
+"""Scope row f1 — linear event augmentations (audiblelight/augmentation.py) on the device.
+
+CPU: the oracle restatement of Fade / Invert / Reverse against golden vectors of the unmodified reference, and
+sanity of the (unpinned) filter formulas. GPU: every op, chains, peak normalisation and an end-to-end render through
+the C-ABI against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from audiblelight_b200 import augment as A
+from oracle import augment_oracle as ao
+from oracle import synth_oracle as orc
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(G, "augment.npz"))
+
+
+# ---- CPU -------------------------------------------------------------------------------------------------------------
+def test_oracle_fade_invert_reverse_match_reference(gold):
+    x = gold["x"]
+    for i, (sr, fi, fo, si, so) in enumerate(gold["fade_cases"]):
+        got = ao.fade(x, sr, fi, fo, ao.FADE_SHAPES[int(si)], ao.FADE_SHAPES[int(so)])
+        assert np.array_equal(got, gold[f"fade_{i}"])          # bit-exact restatement
+    assert np.array_equal(ao.invert(x), gold["invert"])
+    assert np.array_equal(ao.reverse(x), gold["reverse"])
+
+
+def test_fade_endpoints():
+    # tests/test_augmentation.py:303-330 of the reference: a full-length linear fade-in starts at 0 and ends at 1
+    x = np.ones(1000)
+    y = ao.fade(x, 1000, 1.0, 0.0, "linear", "none")
+    assert y[0] == 0.0 and y[-1] == 1.0
+    y = ao.fade(x, 1000, 0.0, 1.0, "none", "linear")
+    assert y[0] == 1.0 and y[-1] == 0.0
+
+
+def test_filter_formulas_sanity():
+    sr = 24000.0
+    w0 = 0.0
+    def resp(b, a, w):
+        z = np.exp(-1j * w * np.arange(3))
+        b = np.array(list(b) + [0] * (3 - len(b))); a = np.array(list(a) + [0] * (3 - len(a)))
+        return abs((b * z).sum() / (a * z).sum())
+    b, a = A.lowpass_coeffs(sr, 3000.0)
+    assert np.isclose(resp(b, a, 0.0), 1.0) and resp(b, a, np.pi) < 1e-9
+    assert np.isclose(resp(b, a, 2 * np.pi * 3000 / sr), 2 ** -0.5, rtol=1e-6)      # -3 dB at the cutoff
+    b, a = A.highpass_coeffs(sr, 500.0)
+    assert resp(b, a, 0.0) < 1e-12 and np.isclose(resp(b, a, np.pi), 1.0)
+    b, a = A.low_shelf_coeffs(sr, 400.0, -12.0, 0.7)
+    assert np.isclose(resp(b, a, 0.0), 10 ** (-12 / 20), rtol=1e-9) and np.isclose(resp(b, a, np.pi), 1.0)
+    b, a = A.high_shelf_coeffs(sr, 4000.0, 6.0, 0.7)
+    assert np.isclose(resp(b, a, np.pi), 10 ** (6 / 20), rtol=1e-9) and np.isclose(resp(b, a, 0.0), 1.0)
+    b, a = A.peak_coeffs(sr, 2000.0, 9.0, 1.0)
+    assert np.isclose(resp(b, a, 2 * np.pi * 2000 / sr), 10 ** (9 / 20), rtol=1e-9)
+    assert np.isclose(resp(b, a, 0.0), 1.0) and np.isclose(resp(b, a, np.pi), 1.0)
+    assert w0 == 0.0
+
+
+def test_deemphasis_inverts_preemphasis():
+    x = np.random.default_rng(0).standard_normal(3000)
+    for coef in (0.0, 0.3, 0.97):
+        assert np.abs(ao.deemphasis(ao.preemphasis(x, coef), coef) - x).max() < 1e-9
+
+
+# ---- GPU -------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def rnd():
+    from audiblelight_b200.renderer import Renderer
+    r = Renderer(0)
+    yield r
+    r.close()
+
+
+def _augment_only(rnd, x, ops, normalize=False):
+    """Runs the device augmentation and returns the dry audio it produced (event rendered without IRs)."""
+    from audiblelight_b200.renderer import EventJob
+    out = np.zeros(len(x), np.float32)
+    job = EventJob(audio=np.ascontiguousarray(x, np.float32), irs=None, n_channels=1, snr=1.0, ref_db=0.0, aug_ops=ops,
+                   normalize_audio=normalize, audio_out=out)
+    rnd.render([job])
+    return out
+
+
+@pytest.mark.gpu
+def test_gpu_fade_invert_reverse_golden(rnd, gold):
+    x = gold["x"]
+    for i, (sr, fi, fo, si, so) in enumerate(gold["fade_cases"]):
+        got = _augment_only(rnd, x, [A.fade(sr, fi, fo, A.FADE_SHAPES[int(si)], A.FADE_SHAPES[int(so)])])
+        assert np.abs(got - gold[f"fade_{i}"]).max() < 2e-6 * np.abs(x).max()
+    assert np.array_equal(_augment_only(rnd, x, [A.invert()]), gold["invert"])
+    assert np.array_equal(_augment_only(rnd, x, [A.reverse()]), gold["reverse"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [100, 511, 512, 513, 6000, 100001])
+def test_gpu_iir_filters_vs_lfilter(rnd, n):
+    sr = 24000.0
+    x = np.random.default_rng(n).standard_normal(n).astype(np.float32)
+    specs = [A.lowpass_coeffs(sr, 6000.0), A.highpass_coeffs(sr, 100.0), A.low_shelf_coeffs(sr, 300.0, -15.0, 0.4),
+             A.high_shelf_coeffs(sr, 5000.0, 8.0, 0.9), A.peak_coeffs(sr, 1500.0, -9.0, 2.0)]
+    for b, a in specs:
+        got = _augment_only(rnd, x, [A.biquad(b, a)])
+        want = ao.biquad(x, b, a)
+        assert np.abs(got - want).max() < 2e-5 * max(1.0, np.abs(want).max())
+    got = _augment_only(rnd, x, [A.gain_db(-7.5)])
+    assert np.abs(got - ao.gain_db(x.astype(np.float64), -7.5)).max() < 1e-6 * np.abs(x).max()
+    for coef in (0.2, 0.97):
+        assert np.abs(_augment_only(rnd, x, [A.preemphasis(coef)]) - ao.preemphasis(x, coef)).max() < 1e-5
+        assert np.abs(_augment_only(rnd, x, [A.deemphasis(coef)]) - ao.deemphasis(x, coef)).max() < 3e-5 * max(1.0, np.abs(ao.deemphasis(x, coef)).max())
+
+
+@pytest.mark.gpu
+def test_gpu_chain_and_normalise(rnd):
+    sr = 24000.0
+    x = np.random.default_rng(5).standard_normal(30000).astype(np.float32)
+    ops = [A.fade(sr, 0.1, 0.2, "half_sine", "exponential"), A.highpass(sr, 200.0)] + \
+        A.multiband_equalizer(sr, [(1200.0, 6.0, 1.0), (5000.0, -4.0, 0.7)]) + [A.invert(), A.gain_db(3.0)]
+    got = _augment_only(rnd, x, ops, normalize=True)
+    y = ao.fade(x.astype(np.float64), sr, 0.1, 0.2, "half_sine", "exponential")
+    y = ao.biquad(y, *A.highpass_coeffs(sr, 200.0))
+    y = ao.biquad(y, *A.peak_coeffs(sr, 1200.0, 6.0, 1.0))
+    y = ao.biquad(y, *A.peak_coeffs(sr, 5000.0, -4.0, 0.7))
+    y = ao.peak_normalize(ao.gain_db(ao.invert(y), 3.0))
+    assert np.isclose(np.abs(got).max(), 1.0, atol=1e-6)
+    assert np.abs(got - y).max() < 2e-5
+
+
+@pytest.mark.gpu
+def test_gpu_render_with_augmentation_equals_render_of_augmented_audio(rnd):
+    """Event.load_audio semantics: augment -> peak-normalise -> render_event_audio (event.py:530-536 + synthesize.py:551)."""
+    from audiblelight_b200.renderer import EventJob, moving_frames
+    sr = 24000.0
+    rng = np.random.default_rng(6)
+    raw = (0.3 * rng.standard_normal(20000)).astype(np.float32)
+    irs = cases.make_irs(rng, 4, 5, 3000)
+    ops = [A.lowpass(sr, 7000.0), A.fade(sr, 0.05, 0.05, "linear", "linear")]
+    job = EventJob(audio=raw, irs=irs.astype(np.float32), n_channels=4, snr=14.0, ref_db=-65.0, aug_ops=ops, normalize_audio=True)
+    job.ir_frames, job.n_frames = moving_frames(20000 / sr, sr, 5, 20000)
+    rnd.render([job])
+    y = ao.fade(ao.biquad(raw, *A.lowpass_coeffs(sr, 7000.0)), sr, 0.05, 0.05, "linear", "linear")
+    y = ao.peak_normalize(y).astype(np.float32)
+    res = orc.render_event(y, irs, 14.0, -65.0, is_moving=True, duration=20000 / sr, sample_rate=sr, literal=False)
+    assert np.abs(job.spatial - res.spatial).max() <= 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_normalise_only_and_silent_audio(rnd):
+    x = np.random.default_rng(7).standard_normal(5000).astype(np.float32) * 0.01
+    got = _augment_only(rnd, x, [], normalize=True)
+    assert np.abs(got - ao.peak_normalize(x)).max() < 1e-6
+    assert np.all(_augment_only(rnd, np.zeros(3000, np.float32), [A.gain_db(6.0)], normalize=True) == 0)   # silent file -> no NaN

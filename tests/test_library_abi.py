@@ -29,7 +29,7 @@ def test_header_symbols_exported_and_bound():
 def test_struct_sizes_match_header():
     from audiblelight_b200 import _lib
     lib = _lib.load()  # load() itself raises on a mismatch
-    for which, mirror in enumerate((_lib.AlrEvent, _lib.AlrScene, _lib.AlrEventStats, _lib.AlrProfile)):
+    for which, mirror in enumerate((_lib.AlrEvent, _lib.AlrScene, _lib.AlrEventStats, _lib.AlrProfile, _lib.AlrAugOp)):
         assert lib.alr_struct_size(which) == C.sizeof(mirror)
     assert lib.alr_struct_size(99) == -1
 
