@@ -43,6 +43,7 @@ struct EvDev {
   int stat;              // index into the stats array
   int part0, nparts;     // range of reduction partials written by k_ifft_ola
   int dry_channel, dry_low, dry_high;
+  const float* xnorm;    // optional scalar the dry audio is multiplied with (peak normalisation), or NULL
   double snr, ref_db;
 };
 
@@ -210,7 +211,7 @@ k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix,
   const IrDev ir = irs[ev.ir0 + l];
   const int j = local - ir.xslot;
   const int t0 = (ir.xb0 + j) * kP;
-  const float sc = irscale[ev.ir0 + l];
+  const float sc = irscale[ev.ir0 + l] * (ev.xnorm ? __ldg(ev.xnorm) : 1.f);
   const float* __restrict__ x = ev.x;
   const float2 zt = __ldg(zeta + t);
   // sin^2(pi p / 256) for the in-frame positions of this thread's samples: offset t + kGroup r inside the block, i.e.
@@ -621,7 +622,7 @@ __global__ void k_tile(const EvDev* __restrict__ evs, const int* __restrict__ li
   const long long total = (long long)ev.C * ev.n_out;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(i % ev.n_out);
-    const float a = n < ev.Lx ? ev.x[n] : 0.f;
+    const float a = n < ev.Lx ? ev.x[n] * (ev.xnorm ? __ldg(ev.xnorm) : 1.f) : 0.f;
     ev.y[i] = a;
     vmax = fmaxf(vmax, fabsf(a));
     vsum += fabsf(a);
@@ -918,27 +919,94 @@ __device__ __forceinline__ void iir_coeffs(const AugDev& o, float& b0, float& b1
     b0 = o.p[0]; b1 = o.p[1]; b2 = o.p[2]; a1 = o.p[3]; a2 = o.p[4];
   }
 }
-__global__ void k_iir_pass1(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix, int n_ops, int n_chunks,
-                            float2* __restrict__ zs) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per chunk streams its samples in 32-sample register tiles: eight independent 16-byte loads per tile (the
+// next tile is requested before the current one is filtered), so ~1000 loads are in flight per CTA and every
+// 128-byte line is consumed by the thread that fetched it. (The first version walked memory sample by sample with a
+// 2 KB stride between lanes and thrashed L1: 3.9 ms per benchmark step; a shared-memory transposing version with
+// only 4 loads in flight per warp still took 1.2 ms.)
+constexpr int kIirCta = 128, kIirSub = 32;
+
+__device__ __forceinline__ void iir_load_tile(const float* __restrict__ src, int n, int n1, bool vec, float (&v)[kIirSub]) {
+  if (vec && n + kIirSub <= n1) {
+#pragma unroll
+    for (int q = 0; q < kIirSub / 4; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src + n) + q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kIirSub; ++j) v[j] = (n + j < n1) ? __ldg(src + n + j) : 0.f;
+  }
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kIirCta)
+k_iir_pass(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix, int n_ops, int n_chunks,
+           float2* __restrict__ zs) {
+  const int c = blockIdx.x * kIirCta + threadIdx.x;
   if (c >= n_chunks) return;
   const int oi = find_segment(chunk_prefix, n_ops, c);
   const AugDev& o = ops[oi];
   float b0, b1, b2, a1, a2;
   iir_coeffs(o, b0, b1, b2, a1, a2);
   const int n0 = (c - chunk_prefix[oi]) * kIirChunk, n1 = min(n0 + kIirChunk, o.L);
-  float s1 = 0.f, s2 = 0.f;
-  for (int n = n0; n < n1; ++n) {
-    const float x = o.src[n];
-    const float y = fmaf(b0, x, s1);
-    s1 = fmaf(b1, x, fmaf(-a1, y, s2));
-    s2 = fmaf(b2, x, -a2 * y);
+  const float* __restrict__ src = o.src;
+  float* __restrict__ dst = o.dst;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+  float s1 = 0.f, s2 = 0.f, corr = 0.f, cpow = 1.f, coef = 0.f;
+  bool deemph = false;
+  if (WRITE) {
+    s1 = zs[c].x;
+    s2 = zs[c].y;
+    // librosa.effects.deemphasis subtracts ((2 - coef) x0 - x1) / (3 - coef) * coef^n afterwards
+    if (o.type == kAugDeemph && o.L > 1) {
+      deemph = true;
+      coef = o.p[0];
+      corr = ((2.f - coef) * src[0] - src[1]) / (3.f - coef);
+      cpow = powf(coef, (float)n0);
+    }
   }
-  zs[c] = make_float2(s1, s2);
+  float cur[kIirSub], nxt[kIirSub];
+  iir_load_tile(src, n0, n1, vec, cur);
+  for (int n = n0; n < n1; n += kIirSub) {
+    if (n + kIirSub < n1) iir_load_tile(src, n + kIirSub, n1, vec, nxt);
+#pragma unroll
+    for (int j = 0; j < kIirSub; ++j) {
+      const float x = cur[j];
+      const float y = fmaf(b0, x, s1);
+      s1 = fmaf(b1, x, fmaf(-a1, y, s2));
+      s2 = fmaf(b2, x, -a2 * y);
+      if (WRITE) {
+        if (deemph) {
+          cur[j] = y - corr * cpow;
+          cpow *= coef;
+        } else {
+          cur[j] = y;
+        }
+      }
+    }
+    if (WRITE) {
+      if (vec && n + kIirSub <= n1) {
+#pragma unroll
+        for (int q = 0; q < kIirSub / 4; ++q)
+          reinterpret_cast<float4*>(dst + n)[q] = make_float4(cur[4 * q], cur[4 * q + 1], cur[4 * q + 2], cur[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kIirSub; ++j)
+          if (n + j < n1) dst[n + j] = cur[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kIirSub; ++j) cur[j] = nxt[j];
+  }
+  if (!WRITE) zs[c] = make_float2(s1, s2);
 }
+
+// One WARP per op: lanes fetch 32 zero-state results at once (one coalesced request instead of 32 dependent
+// round trips), the carry is then chained through the batch from registers with shuffles. blockDim = 128.
 __global__ void k_iir_combine(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix, int n_ops,
                               float2* __restrict__ zs) {
-  const int oi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (oi >= n_ops) return;
   const AugDev& o = ops[oi];
   float b0, b1, b2, a1f, a2f;
@@ -952,56 +1020,52 @@ __global__ void k_iir_combine(const AugDev* __restrict__ ops, const int* __restr
   }
   double s1 = 0.0, s2 = 0.0;  // state entering chunk 0 (pedalboard runs with reset=True; de-emphasis starts from zeros)
   const int c0 = chunk_prefix[oi], c1 = chunk_prefix[oi + 1];
-  for (int c = c0; c < c1; ++c) {
-    const float2 z = zs[c];
-    zs[c] = make_float2((float)s1, (float)s2);  // replace the zero-state result by the true entry state
-    const double t1 = m00 * s1 + m01 * s2 + z.x, t2 = m10 * s1 + m11 * s2 + z.y;
-    s1 = t1;
-    s2 = t2;
-  }
-}
-__global__ void k_iir_pass2(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix, int n_ops, int n_chunks,
-                            const float2* __restrict__ zs) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_chunks) return;
-  const int oi = find_segment(chunk_prefix, n_ops, c);
-  const AugDev& o = ops[oi];
-  float b0, b1, b2, a1, a2;
-  iir_coeffs(o, b0, b1, b2, a1, a2);
-  const int n0 = (c - chunk_prefix[oi]) * kIirChunk, n1 = min(n0 + kIirChunk, o.L);
-  float s1 = zs[c].x, s2 = zs[c].y;
-  // librosa.effects.deemphasis subtracts ((2 - coef) x0 - x1) / (3 - coef) * coef^n afterwards
-  float corr = 0.f, cpow = 1.f;
-  if (o.type == kAugDeemph && o.L > 1) {
-    const float cf = o.p[0];
-    corr = ((2.f - cf) * o.src[0] - o.src[1]) / (3.f - cf);
-    cpow = powf(cf, (float)n0);
-  }
-  for (int n = n0; n < n1; ++n) {
-    const float x = o.src[n];
-    const float y = fmaf(b0, x, s1);
-    s1 = fmaf(b1, x, fmaf(-a1, y, s2));
-    s2 = fmaf(b2, x, -a2 * y);
-    if (o.type == kAugDeemph) {
-      o.dst[n] = y - corr * cpow;
-      cpow *= o.p[0];
-    } else {
-      o.dst[n] = y;
+  for (int cb = c0; cb < c1; cb += 32) {
+    const int c = cb + lane;
+    const float2 z = c < c1 ? zs[c] : make_float2(0.f, 0.f);
+    float in1 = 0.f, in2 = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const float zx = __shfl_sync(0xffffffffu, z.x, j), zy = __shfl_sync(0xffffffffu, z.y, j);
+      if (lane == j) {  // the true entry state of chunk cb + j replaces its zero-state result
+        in1 = (float)s1;
+        in2 = (float)s2;
+      }
+      const double t1 = m00 * s1 + m01 * s2 + zx, t2 = m10 * s1 + m11 * s2 + zy;
+      s1 = t1;
+      s2 = t2;
     }
+    if (c < c1) zs[c] = make_float2(in1, in2);
   }
 }
 
-// peak normalisation of Event.load_audio: x / max(|x| + tiny)   (event.py:535-536). grid = (slices, events)
+// peak normalisation of Event.load_audio: x / max(|x| + tiny)   (event.py:535-536). The reciprocal peak is a per-event
+// SCALAR: it is folded into the source-spectrum scale of k_x_fft (and k_tile) instead of rewriting the audio; only
+// events whose normalised audio is requested back (alr_event.audio_out) are scaled in place.
 struct NormDev {
   float* x;
   int L;
   int part0;
+  int scale_in_place;  // 1: audio_out requested
 };
 __global__ void k_peak_partial(const NormDev* __restrict__ nd, float* __restrict__ partials) {
   __shared__ float s_max[32];
   const NormDev& d = nd[blockIdx.y];
+  const float* __restrict__ x = d.x;
+  const int L = d.L;
   float m = 0.f;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < d.L; n += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(d.x[n]));
+  const int stride = gridDim.x * blockDim.x, i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const int n4 = L >> 2;
+    for (int q = i0; q < n4; q += stride) {
+      const float4 v = __ldg(x4 + q);
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (int n = (n4 << 2) + i0; n < L; n += stride) m = fmaxf(m, fabsf(x[n]));
+  } else {
+    for (int n = i0; n < L; n += stride) m = fmaxf(m, fabsf(x[n]));
+  }
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -1010,12 +1074,19 @@ __global__ void k_peak_partial(const NormDev* __restrict__ nd, float* __restrict
     partials[d.part0 + blockIdx.x] = m;
   }
 }
-__global__ void k_peak_scale(const NormDev* __restrict__ nd, const float* __restrict__ partials, int slices) {
+// xnorm[i] = 1 / (max + tiny(float32)); events with scale_in_place get their audio scaled and xnorm = 1. grid = (slices, events)
+__global__ void k_peak_final(const NormDev* __restrict__ nd, const float* __restrict__ partials, int slices,
+                             float* __restrict__ xnorm) {
   const NormDev& d = nd[blockIdx.y];
   float m = 0.f;
   for (int i = 0; i < slices; ++i) m = fmaxf(m, partials[d.part0 + i]);
-  const float inv = 1.0f / (m + 1.17549435e-38f);  // tiny(float32)
+  const float inv = 1.0f / (m + 1.17549435e-38f);
+  if (!d.scale_in_place) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) xnorm[blockIdx.y] = inv;
+    return;
+  }
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < d.L; n += gridDim.x * blockDim.x) d.x[n] *= inv;
+  if (blockIdx.x == 0 && threadIdx.x == 0) xnorm[blockIdx.y] = 1.0f;
 }
 
 // ---- unit-test kernels for the FFT core ---------------------------------------------------------------------

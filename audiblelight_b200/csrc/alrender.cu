@@ -681,6 +681,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
   };
   std::vector<AudioOut> aug_audio_out;
   int aug_chunks_total = 0, aug_any = 0;
+  std::vector<int> ev_norm_idx(n_events, -1);  // index of the event's peak-normalisation scalar, or -1
   {
     size_t aug_floats = 0;
     for (int64_t i = 0; i < n_events; ++i) {
@@ -743,6 +744,8 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
           nd.x = fin;
           nd.L = L;
           nd.part0 = (int)aug_norm.size() * kAugSlices;
+          nd.scale_in_place = uin.audio_out ? 1 : 0;
+          ev_norm_idx[i] = (int)aug_norm.size();
           aug_norm.push_back(nd);
         }
         if (uin.audio_out) aug_audio_out.push_back({uin.audio_out, fin, (size_t)L * sizeof(float)});
@@ -750,6 +753,21 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       }
     }
   }
+
+  // the augmentation descriptor buffer is sized now (upper bound): the normalisation scalars live at its start and the
+  // event descriptors built below point at them
+  const size_t xnorm_bytes = align_up(std::max<size_t>(aug_norm.size(), 1) * sizeof(float), 256);
+  size_t aug_desc_reserved = 0;
+  if (aug_any) {
+    size_t n_ops_total = 0;
+    for (int l = 0; l < kAugLevels; ++l) n_ops_total += aug_point[l].size() + aug_iir[l].size();
+    aug_desc_reserved = xnorm_bytes + n_ops_total * (sizeof(AugDev) + sizeof(int)) + kAugLevels * 3 * 64 +
+                        aug_norm.size() * sizeof(NormDev) + (size_t)std::max(aug_chunks_total, 1) * sizeof(float2) +
+                        std::max<size_t>(aug_norm.size(), 1) * kAugSlices * sizeof(float) + 4096;
+    int rc = ctx->augdesc.ensure(aug_desc_reserved);
+    if (rc) return rc;
+  }
+  const float* d_xnorm = aug_any ? (const float*)ctx->augdesc.p : nullptr;
 
   // ---- sizes, chunks and buffers (cheap pre-pass; no detailed planning yet) -----------------------------------------
   const auto host_t0 = std::chrono::steady_clock::now();
@@ -1097,6 +1115,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     // descriptor blob: per level [pointwise ops][iir ops][iir chunk prefix], then the normalisation list
     Blob ab;
     size_t off_point[kAugLevels], off_iir[kAugLevels], off_pref[kAugLevels];
+    ab.bytes.resize(xnorm_bytes, 0);  // [0, xnorm_bytes): the per-event normalisation scalars (written by k_peak_final)
     for (int l = 0; l < kAugLevels; ++l) {
       off_point[l] = ab.add(aug_point[l].data(), aug_point[l].size() * sizeof(AugDev));
       off_iir[l] = ab.add(aug_iir[l].data(), aug_iir[l].size() * sizeof(AugDev));
@@ -1106,10 +1125,9 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     const size_t off_zs = align_up(ab.bytes.size(), 256);
     const size_t off_peaks = align_up(off_zs + (size_t)std::max(aug_chunks_total, 1) * sizeof(float2), 256);
     const size_t aug_total = off_peaks + std::max<size_t>(aug_norm.size(), 1) * kAugSlices * sizeof(float);
+    if (aug_total > aug_desc_reserved) return fail(ALR_ERR_INVALID, "internal: augmentation descriptor bound exceeded");
     {
-      int rc = ctx->augdesc.ensure(aug_total);
-      if (rc) return rc;
-      rc = ctx->stage_aug.ensure(ab.bytes.size() + 16);
+      int rc = ctx->stage_aug.ensure(ab.bytes.size() + 16);
       if (rc) return rc;
     }
     memcpy(ctx->stage_aug.p, ab.bytes.data(), ab.bytes.size());
@@ -1132,11 +1150,11 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         const AugDev* dops = (const AugDev*)(ad + off_iir[l]);
         const int* dpref = (const int*)(ad + off_pref[l]);
         // the zero-state scratch is indexed by the level-local chunk number
-        k_iir_pass1<<<ceil_div(n_ch, 128), 128, 0, st>>>(dops, dpref, n_ops, n_ch, d_zs);
+        k_iir_pass<false><<<ceil_div(n_ch, kIirCta), kIirCta, 0, st>>>(dops, dpref, n_ops, n_ch, d_zs);
         LAUNCH_CHECK(kCatOther);
-        k_iir_combine<<<ceil_div(n_ops, 64), 64, 0, st>>>(dops, dpref, n_ops, d_zs);
+        k_iir_combine<<<ceil_div(n_ops, 4), 128, 0, st>>>(dops, dpref, n_ops, d_zs);
         LAUNCH_CHECK(kCatOther);
-        k_iir_pass2<<<ceil_div(n_ch, 128), 128, 0, st>>>(dops, dpref, n_ops, n_ch, d_zs);
+        k_iir_pass<true><<<ceil_div(n_ch, kIirCta), kIirCta, 0, st>>>(dops, dpref, n_ops, n_ch, d_zs);
         LAUNCH_CHECK(kCatOther);
       }
     }
@@ -1146,7 +1164,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         const unsigned cnt = (unsigned)std::min<size_t>(32768, aug_norm.size() - n0);
         k_peak_partial<<<dim3(kAugSlices, cnt), 256, 0, st>>>(dn + n0, d_peaks);
         LAUNCH_CHECK(kCatOther);
-        k_peak_scale<<<dim3(kAugSlices, cnt), 256, 0, st>>>(dn + n0, d_peaks, kAugSlices);
+        k_peak_final<<<dim3(kAugSlices, cnt), 256, 0, st>>>(dn + n0, d_peaks, kAugSlices, (float*)ad + n0);
         LAUNCH_CHECK(kCatOther);
       }
     }
@@ -1187,6 +1205,10 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         int x_used = 0;
         plan_event_into(evl[ei], ph == 0 ? ei : dry_parent[ei], z, d, h_irs + ir_off, ir_off, h_wband + w_off, w_off,
                         h_lr + blk_off, blk_off, &x_used);
+        {
+          const int parent_ev = ph == 0 ? ei : dry_parent[ei];
+          d.xnorm = (d_xnorm && ev_norm_idx[parent_ev] >= 0) ? d_xnorm + ev_norm_idx[parent_ev] : nullptr;
+        }
         if (ph == 1) {
           d.gain_mode = kGainDry;
           d.parent = dry_parent[ei];

@@ -13,6 +13,7 @@ from typing import List, Optional
 
 import numpy as np
 
+from . import augment as _aug
 from .renderer import EventJob, SceneJob, event_slice, moving_frames, scene_samples
 
 
@@ -22,6 +23,7 @@ class EventSpec:
     n_irs: int
     snr: float
     start: float  # seconds
+    aug: Optional[tuple] = None  # one linear augmentation: (kind, cutoff_hz[, gain_db, q]); None = no augmentation
 
 
 @dataclass
@@ -37,7 +39,8 @@ class SceneSpec:
 
 
 def c3_scene_spec(scene_idx: int, sr: int = 24000, duration: float = 60.0, channels: int = 4, lh: int = 24000,
-                  n_static: int = 6, n_moving: int = 3, ir_rate: float = 10.0, ambience: bool = True) -> SceneSpec:
+                  n_static: int = 6, n_moving: int = 3, ir_rate: float = 10.0, ambience: bool = True,
+                  augment: bool = False) -> SceneSpec:
     """DCASE-style SELD scene with moving events (configs[2] / the unit of configs[4]): 60 s @ 24 kHz, 4 channels,
     1 s RIRs, 6 static + 3 moving events of U(2, 10) s, moving events with one RIR per 100 ms, SNR U(5, 30)."""
     rng = np.random.default_rng(1000 + scene_idx)
@@ -50,6 +53,19 @@ def c3_scene_spec(scene_idx: int, sr: int = 24000, duration: float = 60.0, chann
         n_irs = int(round(ir_rate * dur)) + 1 if moving else 1
         events.append(EventSpec(n_audio=n_audio, n_irs=n_irs, snr=float(rng.uniform(5.0, 30.0)),
                                 start=float(rng.uniform(0.0, duration - dur))))
+    if augment:
+        # every event is preceded by ONE linear augmentation with seeded parameters (ranges of
+        # augmentation.py scaled to the 24 kHz Nyquist) and Event.load_audio's peak normalisation. A separate
+        # generator keeps the scene structure identical to the un-augmented workload.
+        arng = np.random.default_rng(9000 + scene_idx)
+        for e in events:
+            kind = ["lowpass", "highpass", "low_shelf", "high_shelf", "peak"][int(arng.integers(0, 5))]
+            if kind == "lowpass":
+                e.aug = (kind, float(arng.uniform(0.125, 0.45) * sr))
+            elif kind == "highpass":
+                e.aug = (kind, float(arng.uniform(32.0, 1024.0)))
+            else:
+                e.aug = (kind, float(arng.uniform(100.0, 0.4 * sr)), float(arng.uniform(-20.0, 10.0)), float(arng.uniform(0.1, 1.0)))
     return SceneSpec(index=scene_idx, sr=sr, duration=duration, channels=channels, n_ir_samples=lh, ref_db=-65.0,
                      events=events, ambience=ambience)
 
@@ -72,6 +88,17 @@ def c4_scene_spec(scene_idx: int = 0) -> SceneSpec:
               for _ in range(5)]
     return SceneSpec(index=scene_idx, sr=48000, duration=30.0, channels=64, n_ir_samples=96000, ref_db=-65.0,
                      events=events, ambience=False)
+
+
+def aug_coeffs(aug: tuple, sr: float):
+    """(b, a) of an EventSpec.aug entry (formulas of audiblelight_b200.augment; shared with the CPU baseline)."""
+    kind = aug[0]
+    if kind == "lowpass":
+        return _aug.lowpass_coeffs(sr, aug[1])
+    if kind == "highpass":
+        return _aug.highpass_coeffs(sr, aug[1])
+    fn = {"low_shelf": _aug.low_shelf_coeffs, "high_shelf": _aug.high_shelf_coeffs, "peak": _aug.peak_coeffs}[kind]
+    return fn(sr, aug[1], aug[2], aug[3])
 
 
 def algorithmic_bytes(spec: SceneSpec) -> int:
@@ -139,6 +166,9 @@ def scene_jobs(spec: SceneSpec, arrays, amb, scene_index: int):
     for e, (x, h) in zip(spec.events, arrays):
         dur = e.n_audio / float(spec.sr)
         j = EventJob(audio=x, irs=h, n_channels=spec.channels, snr=e.snr, ref_db=spec.ref_db, scene=scene_index)
+        if e.aug is not None:
+            j.aug_ops = [_aug.biquad(*aug_coeffs(e.aug, float(spec.sr)))]
+            j.normalize_audio = True
         if e.n_irs > 1:
             j.ir_frames, j.n_frames = moving_frames(dur, float(spec.sr), e.n_irs, e.n_audio)
         j.scene_start, j.scene_end = event_slice(e.start, e.start + dur, spec.sr, T)

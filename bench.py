@@ -111,7 +111,9 @@ class ClockSampler:
 
 def scene_spec(workload: str, idx: int):
     from audiblelight_b200 import workload as wl
-    return {"c5": wl.c3_scene_spec, "c2": wl.c2_scene_spec, "c1": wl.c1_scene_spec, "c4": wl.c4_scene_spec}[workload](idx)
+    if workload == "c5":  # C3-style scene + one linear augmentation per event
+        return wl.c3_scene_spec(idx, augment=True)
+    return {"c2": wl.c2_scene_spec, "c1": wl.c1_scene_spec, "c4": wl.c4_scene_spec}[workload](idx)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -153,7 +155,8 @@ def partition_size():
 
 def config_dict(args, world):
     names = {"c5": "configs[4]: batch of one-minute C3-style SELD scenes with moving events (60 s @ 24 kHz, 4 ch, "
-                   "1 s RIRs, 6 static + 3 moving events, 10 RIR/s, Gaussian ambience), scene-sharded",
+                   "1 s RIRs, 6 static + 3 moving events, 10 RIR/s, one linear augmentation + peak normalisation per "
+                   "event, Gaussian ambience), scene-sharded",
              "c2": "configs[1]: 60 s @ 24 kHz, 4 ch, 9 static events + ambience",
              "c1": "configs[0]: one static 10 s event, 4-ch 1 s RIR",
              "c4": "configs[3]: em64 64 ch, 48 kHz, 2 s RIRs, 5 static events"}

@@ -44,7 +44,8 @@ def _worker(args):
         sys.path.insert(0, root)
     from audiblelight_b200 import workload as wl
     from oracle import synth_oracle as orc
-    spec = wl.c3_scene_spec(scene_idx)
+    from oracle import augment_oracle as ao
+    spec = wl.c3_scene_spec(scene_idx, augment=True)
     # inputs (float64 IRs as the reference's backends deliver them); generation is not timed
     rng = np.random.default_rng(5000 + scene_idx)
     decay = np.exp(-np.arange(spec.n_ir_samples) / (spec.n_ir_samples / 6.0))
@@ -55,6 +56,10 @@ def _worker(args):
     for e in spec.events:
         x = rng.standard_normal(e.n_audio).astype(np.float32)
         x = (x / np.max(np.abs(x) + np.finfo(np.float32).tiny)).astype(np.float32)
+        if e.aug is not None:  # Event.load_audio: augmentation, then peak normalisation (event.py:530-536)
+            t0 = time.perf_counter()
+            x = ao.peak_normalize(ao.biquad(x, *wl.aug_coeffs(e.aug, float(spec.sr)))).astype(np.float32)
+            t_static += time.perf_counter() - t0
         dur = e.n_audio / float(spec.sr)
         if e.n_irs == 1:
             h = rng.standard_normal((spec.channels, 1, spec.n_ir_samples)) * decay

@@ -26,6 +26,9 @@ def _oracle_scene(spec, arrays64, amb):
     spatial, starts, ends = [], [], []
     for e, (x, h) in zip(spec.events, arrays64):
         dur = e.n_audio / float(spec.sr)
+        if e.aug is not None:
+            from oracle import augment_oracle as ao
+            x = ao.peak_normalize(ao.biquad(x, *wl.aug_coeffs(e.aug, float(spec.sr)))).astype(np.float32)
         res = orc.render_event(x, h, e.snr, spec.ref_db, is_moving=e.n_irs > 1, duration=dur, sample_rate=float(spec.sr),
                                literal=False)
         spatial.append(res.spatial)
@@ -70,6 +73,17 @@ def test_config3_moving_scene_60s(rnd):
     for j, s in zip(jobs, spatial):
         err = np.abs(j.spatial - s).max()
         assert err <= TOL and err <= 3e-5 * np.abs(s).max()
+    assert np.abs(sj.mix.astype(np.float64) - mix.scene).max() <= TOL
+
+
+def test_config5_unit_scene_with_augmentations(rnd):
+    """The unit of configs[4] as bench.py runs it: C3 scene + one seeded linear augmentation and peak normalisation per
+    event on the device (f1)."""
+    spec = wl.c3_scene_spec(9, augment=True)
+    assert all(e.aug is not None for e in spec.events)
+    jobs, sj, spatial, mix = _run_scene(rnd, spec)
+    for j, s_ in zip(jobs, spatial):
+        assert np.abs(j.spatial - s_).max() <= TOL
     assert np.abs(sj.mix.astype(np.float64) - mix.scene).max() <= TOL
 
 
