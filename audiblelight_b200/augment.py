@@ -16,7 +16,8 @@ import math
 from dataclasses import dataclass, field
 from typing import List, Sequence, Tuple
 
-ALR_AUG_GAIN, ALR_AUG_INVERT, ALR_AUG_REVERSE, ALR_AUG_FADE, ALR_AUG_BIQUAD, ALR_AUG_PREEMPHASIS, ALR_AUG_DEEMPHASIS = range(7)
+(ALR_AUG_GAIN, ALR_AUG_INVERT, ALR_AUG_REVERSE, ALR_AUG_FADE, ALR_AUG_BIQUAD, ALR_AUG_PREEMPHASIS, ALR_AUG_DEEMPHASIS,
+ ALR_AUG_DELAY) = range(8)
 FADE_SHAPES = ["linear", "exponential", "logarithmic", "quarter_sine", "half_sine", "none"]  # augmentation.py FADE_SHAPES
 
 
@@ -145,3 +146,11 @@ def preemphasis(coef: float) -> AugOp:
 def deemphasis(coef: float) -> AugOp:
     """librosa.effects.deemphasis (augmentation.py:1388-1400)."""
     return AugOp(ALR_AUG_DEEMPHASIS, (float(coef),))
+
+
+def delay(sample_rate: float, delay_seconds: float, feedback: float, mix: float) -> AugOp:
+    """Delay (augmentation.py:1046-1102 -> pedalboard.Delay): integer delay line of int(delay_seconds * sample_rate)
+    samples with feedback and a linear dry/wet mix. Parity UNPINNED (pedalboard is not available offline)."""
+    if not 0.0 <= feedback <= 1.0 or not 0.0 <= mix <= 1.0:
+        raise ValueError("feedback and mix must lie in [0, 1]")
+    return AugOp(ALR_AUG_DELAY, (float(int(delay_seconds * sample_rate)), float(feedback), float(mix)))

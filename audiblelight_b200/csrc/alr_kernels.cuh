@@ -834,7 +834,8 @@ k_mix(const SceneDev* __restrict__ scenes, const AmbDev* __restrict__ ambs, cons
 // ------------------------------------------------------------------------------------------------------------
 // f1: linear event augmentations on the dry audio (audiblelight/augmentation.py, applied by Event.load_audio,
 // event.py:530-536). Every op reads `src` and writes `dst` (ping-pong), so Reverse needs no in-place swap.
-enum { kAugGain = 0, kAugInvert = 1, kAugReverse = 2, kAugFade = 3, kAugBiquad = 4, kAugPreemph = 5, kAugDeemph = 6 };
+enum { kAugGain = 0, kAugInvert = 1, kAugReverse = 2, kAugFade = 3, kAugBiquad = 4, kAugPreemph = 5, kAugDeemph = 6,
+       kAugDelay = 7 };
 constexpr int kIirChunk = 512;  // samples per thread of the chunked IIR scan
 
 struct AugDev {       // one (event, op) application
@@ -878,6 +879,28 @@ __device__ __forceinline__ float fade_out_curve(int shape, float f) {
 __global__ void k_aug_pointwise(const AugDev* __restrict__ ops) {
   const AugDev& o = ops[blockIdx.y];
   const int L = o.L;
+  if (o.type == kAugDelay) {
+    // pedalboard.Delay: every sample pops the delay line (d[n] = w[n-D]), pushes w[n] = x[n] + feedback d[n] and
+    // outputs (1 - mix) x[n] + mix d[n]. The D residue classes n = r (mod D) are independent first-order recurrences
+    // d[n] = x[n-D] + feedback d[n-D]: one thread per residue, coalesced across r.
+    const int D = (int)o.p[0];
+    const float fb = o.p[1], wet = o.p[2], dry = 1.f - o.p[2];
+    if (D <= 0) {
+      for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < L; n += gridDim.x * blockDim.x) o.dst[n] = o.src[n];
+      return;
+    }
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < min(D, L); r += gridDim.x * blockDim.x) {
+      float xp = 0.f, dp = 0.f;  // x[n-D], d[n-D]
+      for (int n = r; n < L; n += D) {
+        const float x = o.src[n];
+        const float d = (n >= D) ? fmaf(fb, dp, xp) : 0.f;
+        o.dst[n] = fmaf(wet, d, dry * x);
+        xp = x;
+        dp = d;
+      }
+    }
+    return;
+  }
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < L; n += gridDim.x * blockDim.x) {
     float v;
     switch (o.type) {

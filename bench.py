@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="c5", choices=["c5", "c2", "c1", "c4"])
     ap.add_argument("--cpu-workers", type=int, default=None)
+    ap.add_argument("--workspace-mb", type=int, default=None, help="override the renderer's workspace limit (experiments)")
     return ap.parse_args()
 
 
@@ -209,7 +210,8 @@ def main():
     b_alg = sum(wl.algorithmic_bytes(sp) for sp in specs)
     b_ir = sum(wl.ir_bytes(sp) for sp in specs)
     scene_seconds = sum(sp.duration for sp in specs)
-    rnd = Renderer(local_rank, profiling=True)
+    rnd = Renderer(local_rank, profiling=True,
+                   workspace_limit=None if args.workspace_mb is None else args.workspace_mb << 20)
     packed = rnd.pack(jobs, scenes)
     stream = torch.cuda.current_stream().cuda_stream
 

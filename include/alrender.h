@@ -67,7 +67,10 @@ enum {
   ALR_AUG_BIQUAD = 4,      /* y[n] = p0 x[n] + p1 x[n-1] + p2 x[n-2] - p3 y[n-1] - p4 y[n-2], zero initial state
                               (Low/HighpassFilter :303/:406 first order; Low/HighShelfFilter :348/:449; PeakFilter :643) */
   ALR_AUG_PREEMPHASIS = 5, /* librosa.effects.preemphasis(coef = p[0])   (:1350) */
-  ALR_AUG_DEEMPHASIS = 6   /* librosa.effects.deemphasis(coef = p[0])    (:1388) */
+  ALR_AUG_DEEMPHASIS = 6,  /* librosa.effects.deemphasis(coef = p[0])    (:1388) */
+  ALR_AUG_DELAY = 7        /* feedback delay (Delay, :1046, pedalboard.Delay): D = p[0] = int(delay_seconds * sr) samples,
+                              d[n] = x[n-D] + p[1] d[n-D] (p[1] = feedback), y[n] = (1 - p[2]) x[n] + p[2] d[n] (p[2] = mix);
+                              D == 0: y = x */
 };
 enum { ALR_FADE_LINEAR = 0, ALR_FADE_EXPONENTIAL = 1, ALR_FADE_LOGARITHMIC = 2, ALR_FADE_QUARTER_SINE = 3,
        ALR_FADE_HALF_SINE = 4, ALR_FADE_NONE = 5 };
@@ -178,7 +181,7 @@ int alr_struct_size(int which);
 int alr_create(int device, alr_context** out);
 void alr_destroy(alr_context* ctx);
 
-/* Upper bound for the spectra workspace (bytes); work is cut into chunks that fit. Default 2 GiB. */
+/* Upper bound for the spectra workspace (bytes); work is cut into chunks that fit. Default 4 GiB (device inputs; host inputs use at most 512 MiB so that transfers pipeline). */
 int alr_set_workspace_limit(alr_context* ctx, int64_t bytes);
 /* 1: record per-kernel CUDA-event timings into alr_profile (adds event records, no syncs). Default 0. */
 int alr_set_profiling(alr_context* ctx, int enable);

@@ -94,3 +94,20 @@ def peak_normalize(x):
     x = np.asarray(x)
     tiny = np.finfo(x.dtype if np.issubdtype(x.dtype, np.floating) else np.float32).tiny
     return x / np.max(np.abs(x) + tiny)
+
+
+def delay(x, sample_rate, delay_seconds, feedback, mix):
+    """pedalboard 0.9.17 Delay (Delay.h process loop, restated; JUCE DelayLine without interpolation): per sample
+    d = pop(); push(x + feedback * d); y = (1 - mix) * x + mix * d, with an integer delay of int(delay_seconds * sr)."""
+    x = np.asarray(x, dtype=np.float64)
+    D = int(delay_seconds * sample_rate)
+    if D == 0:
+        return x.copy()
+    n = x.shape[-1]
+    line = np.zeros(n + D)  # line[k] = value pushed at sample k
+    y = np.empty(n)
+    for i in range(n):
+        d = line[i - D] if i >= D else 0.0
+        line[i] = x[i] + feedback * d
+        y[i] = (1.0 - mix) * x[i] + mix * d
+    return y

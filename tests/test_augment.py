@@ -68,6 +68,23 @@ def test_deemphasis_inverts_preemphasis():
         assert np.abs(ao.deemphasis(ao.preemphasis(x, coef), coef) - x).max() < 1e-9
 
 
+def test_delay_oracle_is_a_feedback_comb():
+    # impulse in -> dry tap at 0, wet taps mix * feedback^(k-1) at k * D
+    x = np.zeros(50)
+    x[0] = 1.0
+    y = ao.delay(x, 10.0, 1.2, 0.5, 0.25)  # D = 12
+    want = np.zeros(50)
+    want[0] = 0.75
+    for k in range(1, 5):
+        want[12 * k] = 0.25 * 0.5 ** (k - 1)
+    assert np.allclose(y, want, atol=1e-15)
+    assert np.array_equal(ao.delay(x, 10.0, 0.0, 0.0, 0.3), x)
+    op = A.delay(24000.0, 0.0123, 0.4, 0.3)
+    assert op.type == A.ALR_AUG_DELAY and op.p[0] == float(int(0.0123 * 24000.0))
+    with pytest.raises(ValueError):
+        A.delay(24000.0, 0.1, 1.5, 0.3)
+
+
 # ---- GPU -------------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def rnd():
@@ -113,6 +130,16 @@ def test_gpu_iir_filters_vs_lfilter(rnd, n):
     for coef in (0.2, 0.97):
         assert np.abs(_augment_only(rnd, x, [A.preemphasis(coef)]) - ao.preemphasis(x, coef)).max() < 1e-5
         assert np.abs(_augment_only(rnd, x, [A.deemphasis(coef)]) - ao.deemphasis(x, coef)).max() < 3e-5 * max(1.0, np.abs(ao.deemphasis(x, coef)).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,delay_s", [(100, 0.001), (5000, 0.01), (5000, 0.5), (100001, 0.0371), (3000, 0.0)])
+def test_gpu_delay_vs_oracle(rnd, n, delay_s):
+    sr = 24000.0
+    x = np.random.default_rng(n).standard_normal(n).astype(np.float32)
+    got = _augment_only(rnd, x, [A.delay(sr, delay_s, 0.45, 0.35)])
+    want = ao.delay(x, sr, delay_s, 0.45, 0.35)
+    assert np.abs(got - want).max() < 2e-6 * np.abs(want).max()
 
 
 @pytest.mark.gpu
