@@ -154,3 +154,54 @@ def delay(sample_rate: float, delay_seconds: float, feedback: float, mix: float)
     if not 0.0 <= feedback <= 1.0 or not 0.0 <= mix <= 1.0:
         raise ValueError("feedback and mix must lie in [0, 1]")
     return AugOp(ALR_AUG_DELAY, (float(int(delay_seconds * sample_rate)), float(feedback), float(mix)))
+
+
+# ---- mapping from the reference's Augmentation objects ---------------------------------------------------------------------
+def from_reference(aug) -> "List[AugOp] | None":
+    """Device ops equivalent to one `audiblelight.augmentation.EventAugmentation` instance, or None when the effect is
+    not a linear filter the device implements (compressors, pitch shift, time warps, codecs ... stay on the host).
+    Dispatch is by class name and the instance's own `params` dict / `sample_rate` (augmentation.py: `self.params`
+    of every class), so nothing from the reference package needs importing."""
+    name = type(aug).__name__
+    p = dict(getattr(aug, "params", {}) or {})
+    sr = float(getattr(aug, "sample_rate", 0.0) or 0.0)
+    try:
+        if name == "LowpassFilter":
+            return [lowpass(sr, p["cutoff_frequency_hz"])]
+        if name == "HighpassFilter":
+            return [highpass(sr, p["cutoff_frequency_hz"])]
+        if name == "LowShelfFilter":
+            return [low_shelf(sr, p["cutoff_frequency_hz"], p["gain_db"], p["q"])]
+        if name == "HighShelfFilter":
+            return [high_shelf(sr, p["cutoff_frequency_hz"], p["gain_db"], p["q"])]
+        if name == "MultibandEqualizer":
+            return multiband_equalizer(sr, list(zip(p["cutoff_frequency_hz"], p["gain_db"], p["q"])))
+        if name == "Gain":
+            return [gain_db(p["gain_db"])]
+        if name == "Invert":
+            return [invert()]
+        if name == "Reverse":
+            return [reverse()]
+        if name == "Preemphasis":
+            return [preemphasis(p["coef"])]
+        if name == "Deemphasis":
+            return [deemphasis(p["coef"])]
+        if name == "Fade":
+            return [fade(sr, p["fade_in_len"], p["fade_out_len"], p["fade_in_shape"], p["fade_out_shape"])]
+        if name == "Delay":
+            return [delay(sr, p["delay_seconds"], p["feedback"], p["mix"])]
+    except (KeyError, TypeError, ValueError):
+        return None
+    return None
+
+
+def chain_from_reference(augmentations, max_ops: int = 8) -> "List[AugOp] | None":
+    """Op list for `Event.augmentations` (applied in order, event.py:530-532), or None if any entry is unsupported or
+    the chain is longer than the device's limit."""
+    ops: List[AugOp] = []
+    for aug in augmentations:
+        o = from_reference(aug)
+        if o is None:
+            return None
+        ops += o
+    return ops if len(ops) <= max_ops else None

@@ -63,6 +63,7 @@ struct EvStat {
 
 struct SceneDev {
   float* mix;
+  short* pcm;  // optional (T, C) interleaved 16-bit copy of the mix
   int C;
   int n_amb;
   long long T;
@@ -1110,6 +1111,27 @@ __global__ void k_peak_final(const NormDev* __restrict__ nd, const float* __rest
   }
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < d.L; n += gridDim.x * blockDim.x) d.x[n] *= inv;
   if (blockIdx.x == 0 && threadIdx.x == 0) xnorm[blockIdx.y] = 1.0f;
+}
+
+// (C, T) float mix -> (T, C) interleaved PCM_16 as libsndfile writes it for sf.write(path, mix.T, sr): psf_lrintf(x * 0x7FFF)
+// stored in a short (round to nearest even, 16-bit truncation, no clipping). grid = (ceil(T / 256), scenes)
+__global__ void k_pcm16(const SceneDev* __restrict__ scenes) {
+  const SceneDev& s = scenes[blockIdx.y];
+  if (!s.pcm) return;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= s.T) return;
+  const int C = s.C;
+  short* __restrict__ out = s.pcm + t * C;
+  if (C == 4 && (reinterpret_cast<uintptr_t>(s.pcm) & 7u) == 0) {
+    short4 v;
+    v.x = (short)__float2int_rn(s.mix[t] * 32767.f);
+    v.y = (short)__float2int_rn(s.mix[s.T + t] * 32767.f);
+    v.z = (short)__float2int_rn(s.mix[2 * s.T + t] * 32767.f);
+    v.w = (short)__float2int_rn(s.mix[3 * s.T + t] * 32767.f);
+    *reinterpret_cast<short4*>(out) = v;
+    return;
+  }
+  for (int c = 0; c < C; ++c) out[c] = (short)__float2int_rn(s.mix[(long long)c * s.T + t] * 32767.f);
 }
 
 // ---- unit-test kernels for the FFT core ---------------------------------------------------------------------

@@ -561,7 +561,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     bool done = false;
   };
   std::vector<OutCopy> out_spatial(mem_space == ALR_MEM_HOST ? n_events : 0), out_dry(mem_space == ALR_MEM_HOST ? n_events : 0);
-  std::vector<OutCopy> out_mix;
+  std::vector<OutCopy> out_mix, out_pcm;
   std::vector<InCopy> in_copies;   // event inputs, in event order
   std::vector<InCopy> amb_copies;  // ambience layers, `ev` holds the scene index; in scene order
   const bool host_mode = mem_space == ALR_MEM_HOST;
@@ -577,7 +577,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     std::vector<size_t> off_audio(n_events), off_irs(n_events), off_sp(n_events), off_dry(n_events);
     for (int64_t i = 0; i < n_events; ++i) {
       alr_event& u = events[i];
-      if (!u.spatial || u.n_out < 1 || u.n_channels < 1)
+      if (u.n_out < 1 || u.n_channels < 1 || (!u.spatial && (u.scene < 0 || u.n_irs == -1)))
         return fail(ALR_ERR_INVALID, "event %d: missing buffers", (int)i);
       if (u.n_irs == -1) {
         size_t bytes = (size_t)u.n_channels * u.n_out * sizeof(float);
@@ -611,11 +611,11 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       off_sp[i] = reserve((size_t)u.n_channels * u.n_out * sizeof(float));
       if (u.dry) off_dry[i] = reserve((size_t)(u.n_audio + u.n_ir_samples - 1) * sizeof(float));
     }
-    std::vector<size_t> off_mix(n_scenes);
+    std::vector<size_t> off_mix(n_scenes), off_pcm(n_scenes);
     std::vector<std::vector<size_t>> off_amb(n_scenes);
     for (int64_t s = 0; s < n_scenes; ++s) {
       alr_scene& u = scenes[s];
-      if (u.n_channels < 1 || u.n_samples < 1 || !u.mix) return fail(ALR_ERR_INVALID, "scene %d: bad shape", (int)s);
+      if (u.n_channels < 1 || u.n_samples < 1 || (!u.mix && !u.pcm16)) return fail(ALR_ERR_INVALID, "scene %d: bad shape", (int)s);
       size_t bytes = (size_t)u.n_channels * u.n_samples * sizeof(float);
       for (int a = 0; a < u.n_ambience; ++a) {
         const float* p = amb_ptrs[s][a];
@@ -632,6 +632,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         off_amb[s].push_back(off);
       }
       off_mix[s] = reserve(bytes);
+      if (u.pcm16) off_pcm[s] = reserve(bytes / 2);
     }
     int rc = ctx->arena.ensure(total);
     if (rc) return rc;
@@ -666,6 +667,12 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       for (int a = 0; a < u.n_ambience; ++a) amb_ptrs[s][a] = (const float*)(base + off_amb[s][a]);
       out_mix.push_back({u.mix, base + off_mix[s], (size_t)u.n_channels * u.n_samples * sizeof(float)});
       u.mix = (float*)(base + off_mix[s]);
+      if (u.pcm16) {
+        out_pcm.push_back({u.pcm16, base + off_pcm[s], (size_t)u.n_channels * u.n_samples * sizeof(int16_t)});
+        u.pcm16 = (int16_t*)(base + off_pcm[s]);
+      } else {
+        out_pcm.push_back({nullptr, nullptr, 0});
+      }
     }
   }
 
@@ -828,6 +835,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     }
   // ---- scene / ambience / mix descriptors (independent of the event plans) ------------------------------------------
   std::vector<SceneDev> h_scenes(n_scenes);
+  bool any_pcm = false;
   std::vector<AmbDev> h_ambs;
   std::vector<MixEv> h_mevs;
   int n_amb_parts = 0;
@@ -839,6 +847,8 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     SceneDev& d = h_scenes[sidx];
     memset(&d, 0, sizeof(d));
     d.mix = u.mix;
+    d.pcm = u.pcm16;
+    any_pcm |= u.pcm16 != nullptr;
     d.C = u.n_channels;
     d.T = u.n_samples;
     d.n_amb = u.n_ambience;
@@ -1075,9 +1085,15 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       const int cnt = std::min(32768, s1 - sidx);
       k_mix<<<dim3(ceil_div(max_t, 1024), cnt), 256, 0, st>>>(d_scenes + sidx, d_ambs, d_mevs);
       LAUNCH_CHECK(kCatMix);
+      if (any_pcm) {
+        k_pcm16<<<dim3(ceil_div(max_t, 256), cnt), 256, 0, st>>>(d_scenes + sidx);
+        LAUNCH_CHECK(kCatMix);
+      }
     }
     if (host_mode) {
       int rc = download_after_compute(out_mix.data() + s0, (size_t)(s1 - s0));
+      if (rc) return rc;
+      rc = download_after_compute(out_pcm.data() + s0, (size_t)(s1 - s0));
       if (rc) return rc;
     }
     scenes_mixed = s1;

@@ -73,6 +73,7 @@ class EventJob:
     aug_ops: Sequence[object] = ()        # list of augment.AugOp, applied in order
     normalize_audio: bool = False         # then x / max(|x| + tiny) as Event.load_audio(normalize=True)
     audio_out: object = None              # optional (Lx,) float32 out: the augmented / normalised dry audio
+    keep_spatial: bool = True             # False (host arrays, mixed events only): render + mix on the device, no copy back
 
 
 @dataclass
@@ -83,6 +84,8 @@ class SceneJob:
     ambience: Sequence[object] = ()       # each (C, T) float32
     ambience_ref_db: Sequence[float] = ()
     mix: object = None                    # (C, T) float32 out
+    pcm16: object = None                  # optional (T, C) int16 out: the PCM_16 samples sf.write(path, mix.T, sr) stores
+    keep_mix: bool = True                 # False (host arrays, pcm16 given): only the PCM copy is downloaded
 
 
 def _is_torch(a) -> bool:
@@ -209,9 +212,13 @@ class Renderer:
                 a.gain_mode = int(e.gain_mode)
                 a.snr = float(e.snr)
                 a.ref_db = float(e.ref_db)
-                if e.spatial is None:
+                if not e.keep_spatial:
+                    if _is_torch(e.audio) or e.scene < 0:
+                        raise ValueError("keep_spatial=False needs host arrays and an event that is mixed into a scene")
+                    e.spatial = None
+                elif e.spatial is None:
                     e.spatial = self._alloc_like(e.audio, (C_, n_out))
-                if tuple(e.spatial.shape) != (C_, n_out):
+                if e.spatial is not None and tuple(e.spatial.shape) != (C_, n_out):
                     raise ValueError(f"spatial buffer has shape {tuple(e.spatial.shape)}, expected {(C_, n_out)}")
                 a.spatial = _ptr(e.spatial)
                 a.n_out = n_out
@@ -245,6 +252,17 @@ class Renderer:
                 keep += [ptrs, dbs]
                 b.ambience = C.cast(ptrs, C.c_void_p)
                 b.ambience_ref_db = C.cast(dbs, C.c_void_p)
+            if s.pcm16 is not None:
+                if tuple(s.pcm16.shape) != (s.n_samples, s.n_channels) or "int16" not in str(s.pcm16.dtype):
+                    raise ValueError("pcm16 must be an int16 array of shape (n_samples, n_channels)")
+                if not (s.pcm16.is_contiguous() if _is_torch(s.pcm16) else s.pcm16.flags.c_contiguous):
+                    raise ValueError("pcm16 must be contiguous")
+                b.pcm16 = _ptr(s.pcm16)
+            if not s.keep_mix:
+                if s.pcm16 is None or _is_torch(s.pcm16):
+                    raise ValueError("keep_mix=False needs a host pcm16 buffer")
+                b.mix = 0
+                continue
             if s.mix is None:
                 ref = s.ambience[0] if n_amb else next((e.spatial for e in events if e.spatial is not None), None)
                 if ref is None:

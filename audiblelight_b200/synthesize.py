@@ -27,6 +27,7 @@ except Exception:  # pragma: no cover
 
     logger = logging.getLogger("audiblelight_b200")
 
+from . import augment as _augment
 from .renderer import (ALR_GAIN_EVENT, ALR_GAIN_NONE, FFT_SIZE, HOP_SIZE, WIN_SIZE, EventJob, Renderer, SceneJob,
                        event_slice, moving_frames, scene_samples)
 
@@ -41,6 +42,20 @@ except Exception:
 
 _renderers = {}
 _lock = threading.Lock()
+
+# f1 (opt-in): run Event.augmentations on the device when every entry is a linear filter the library implements.
+# Off by default because the IIR effects wrap pedalboard / librosa, which are not available offline: their device
+# arithmetic follows the published formulas but is not pinned against the real dependencies (see augment.py).
+DEVICE_AUGMENTATIONS = False
+
+
+def _load_raw_audio(event) -> np.ndarray:
+    """The first half of Event.load_audio (event.py:519-527): the resampled mono clip BEFORE augmentation and
+    normalisation, with the reference's own loader call."""
+    import librosa  # the reference's dependency; present wherever Event objects exist
+    audio_raw, _ = librosa.load(event.filepath, sr=event.sample_rate, mono=True, offset=event.event_start,
+                                duration=event.duration, dtype=np.float32)
+    return audio_raw
 
 
 def get_renderer(device: int = -1) -> Renderer:
@@ -130,10 +145,23 @@ def time_variant_convolution(irs: np.ndarray, event, fft_size=FFT_SIZE, win_size
 def _event_job(event, irs: np.ndarray, ref_db, ignore_cache: bool) -> EventJob:
     """Everything render_event_audio does on the host before the arithmetic (synthesize.py:544-587)."""
     n_ch, n_emitters, n_ir_samples = irs.shape
-    audio = event.load_audio(ignore_cache=ignore_cache, normalize=True)
-    _valid_audio(audio)
-    n_audio = audio.shape[0]
-    job = EventJob(audio=_as_f32(audio), n_channels=n_ch, snr=float(event.snr), ref_db=float(ref_db), n_out=n_audio)
+    ops = None
+    augs = list(getattr(event, "augmentations", None) or [])
+    cached = bool(getattr(event, "is_audio_loaded", False)) and not ignore_cache
+    if DEVICE_AUGMENTATIONS and augs and not cached:
+        ops = _augment.chain_from_reference(augs)
+    if ops is not None:
+        # the device applies the chain and the peak normalisation of Event.load_audio (event.py:530-536)
+        audio = _load_raw_audio(event)
+        _valid_audio(audio)
+        n_audio = audio.shape[0]
+        job = EventJob(audio=_as_f32(audio), n_channels=n_ch, snr=float(event.snr), ref_db=float(ref_db), n_out=n_audio,
+                       aug_ops=ops, normalize_audio=True, audio_out=np.empty(n_audio, dtype=np.float32))
+    else:
+        audio = event.load_audio(ignore_cache=ignore_cache, normalize=True)
+        _valid_audio(audio)
+        n_audio = audio.shape[0]
+        job = EventJob(audio=_as_f32(audio), n_channels=n_ch, snr=float(event.snr), ref_db=float(ref_db), n_out=n_audio)
     if n_emitters == 1:
         if event.is_moving:
             raise ValueError("Moving Event has only one emitter!")
@@ -174,6 +202,9 @@ def _store_event_result(event, job: EventJob, mic_alias: str) -> None:
     n_ch, n_audio = job.n_channels, job.audio.shape[0]
     if job.stats["nonfinite"]:
         raise ParameterError("Audio buffer is not finite everywhere")
+    if job.audio_out is not None:  # device-side augmentation: what Event.load_audio would have cached (event.py:538)
+        _valid_audio(job.audio_out)
+        event.audio = job.audio_out
     spatial = job.spatial.astype(np.float64) if job.irs is not None else job.spatial  # N == 0 stays float32 (:577)
     _validate_shape(spatial.shape, (n_ch, n_audio))
     event.spatial_audio[mic_alias] = spatial
@@ -341,10 +372,20 @@ def generate_scene_audio_from_events(scene) -> None:
 
 
 # ---- batch entry: many scenes, render + mix in one GPU call ----------------------------------------------------------------
-def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1, store_padded: bool = True) -> None:
+def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1, store_padded: bool = True,
+                  pcm16: bool = False, keep_event_audio: bool = True, keep_mix: bool = True):
     """Renders and mixes a whole batch of Scene objects with one `alr_render` call (events are rendered and mixed
     on the device without a host round trip). Equivalent to calling `render_audio_for_all_scene_events(scene,
-    ignore_cache)` and `generate_scene_audio_from_events(scene)` on every scene."""
+    ignore_cache)` and `generate_scene_audio_from_events(scene)` on every scene.
+
+    Dataset generation (audiblelight_b200.dataset) only needs the mix as the 16-bit PCM that `Scene.generate` writes:
+    `pcm16=True` also returns, per scene, `{mic_alias: (T, C) int16}` packed on the device; `keep_event_audio=False`
+    leaves `event.spatial_audio` (and the padded copies) unset and `keep_mix=False` leaves `scene.audio` unset, so
+    that neither is copied back from the GPU."""
+    if not keep_mix and not pcm16:
+        raise ValueError("keep_mix=False needs pcm16=True")
+    if not keep_event_audio:
+        store_padded = False
     all_jobs: List[EventJob] = []
     all_scenes: List[SceneJob] = []
     book = []
@@ -364,21 +405,33 @@ def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1,
                 j.scene, j.scene_start, j.scene_end = len(all_scenes), s0, s1
                 if j.n_channels != sjob.n_channels and s1 > s0:
                     raise ValueError("all events of a microphone must have the same number of channels")
+                if not keep_event_audio and not j.prerendered and j.dry is None:
+                    j.keep_spatial = False
+            if pcm16:
+                sjob.pcm16 = np.empty((sjob.n_samples, sjob.n_channels), dtype=np.int16)
+                sjob.keep_mix = keep_mix
             all_jobs += mic_jobs
             all_scenes.append(sjob)
             book.append((scene, mic_alias, sjob, mic_jobs, placements))
     start = time()
     get_renderer(device).render(all_jobs, all_scenes)
+    packed = {id(scene): OrderedDict() for scene in scenes}
     for scene, mic_alias, sjob, mic_jobs, placements in book:
         for j, (event, s0, s1) in zip(mic_jobs, placements):
-            if not j.prerendered:
+            if j.stats is not None and j.stats["nonfinite"]:
+                raise ParameterError("Audio buffer is not finite everywhere")
+            if not j.prerendered and j.keep_spatial:
                 _store_event_result(event, j, mic_alias)
             if store_padded and s1 > s0:
                 _store_padded(event, mic_alias, event.spatial_audio[mic_alias], s0, s1, sjob.n_channels,
                               sjob.n_samples, event._spatial_audio_dry.get(mic_alias))
-        _valid_audio(sjob.mix)
-        scene.audio[mic_alias] = sjob.mix
+        if sjob.keep_mix:
+            _valid_audio(sjob.mix)
+            scene.audio[mic_alias] = sjob.mix
+        if pcm16:
+            packed[id(scene)][mic_alias] = sjob.pcm16
     logger.info(f"Rendered scene audio in {(time() - start):.2f} seconds!")
+    return [packed[id(scene)] for scene in scenes] if pcm16 else None
 
 
 # ---- installation into the reference package -----------------------------------------------------------------------------------
@@ -387,10 +440,13 @@ _PATCHED = ("render_event_audio", "render_audio_for_all_scene_events", "generate
 _originals = {}
 
 
-def install() -> None:
+def install(device_augmentations: bool = False) -> None:
     """Rebinds the hot-path functions on `audiblelight.synthesize`. `Scene.generate` imports them at call time
-    (core.py:1828-1831), so every existing caller (tests, scripts/seld/generate_dataset.py) picks them up."""
+    (core.py:1828-1831), so every existing caller (tests, scripts/seld/generate_dataset.py) picks them up.
+    `device_augmentations=True` additionally moves linear `Event.augmentations` chains onto the GPU (f1)."""
     import audiblelight.synthesize as ref  # noqa
+    global DEVICE_AUGMENTATIONS
+    DEVICE_AUGMENTATIONS = bool(device_augmentations)
     g = globals()
     for name in _PATCHED:
         if name not in _originals:

@@ -118,7 +118,9 @@ typedef struct alr_event {
   int32_t reserved0;
   float* dry;               /* out (n_audio + n_ir_samples - 1) -> event._spatial_audio_dry[mic] */
   /* ---- output ---- */
-  float* spatial;           /* out (n_channels, n_out) row-major -> event.spatial_audio[mic] */
+  float* spatial;           /* out (n_channels, n_out) row-major -> event.spatial_audio[mic]. With ALR_MEM_HOST it may be
+                               NULL for an event that is mixed into a scene (scene >= 0): the event is rendered and mixed
+                               on the device and never copied back (dataset generation keeps only the mix) */
   int64_t n_out;            /* samples per channel to produce: n_audio for render_event_audio (pad_or_truncate,
                                :590); n_audio+n_ir_samples-1 for the raw static convolution */
   /* ---- placement in a scene mix (generate_scene_audio_from_events, synthesize.py:359-378) ---- */
@@ -140,7 +142,11 @@ typedef struct alr_scene {
   int64_t n_samples;             /* T = round(scene.duration * sr) (:331) */
   const float* const* ambience;  /* HOST array of n_ambience pointers, each (C, T) float32 == Ambience.load_ambience() */
   const double* ambience_ref_db; /* HOST array (n_ambience) */
-  float* mix;                    /* out (C, T) float32 -> scene.audio[mic] */
+  float* mix;                    /* out (C, T) float32 -> scene.audio[mic]. With ALR_MEM_HOST it may be NULL when pcm16
+                                    is given (only the PCM copy is downloaded) */
+  int16_t* pcm16;                /* optional out (T, C) interleaved 16-bit PCM: the sample data Scene.generate stores with
+                                    sf.write(path, mix.T, sr) (core.py:1840-1847; libsndfile's default WAV subtype PCM_16,
+                                    float -> short as lrintf(x * 32767) truncated to 16 bits, no clipping). NULL = none */
 } alr_scene;
 
 /* Per-event numbers the host layer needs back (always HOST memory). */

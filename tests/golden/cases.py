@@ -91,3 +91,65 @@ def scene_inputs(spec):
         evs.append((audio, irs))
     ambs = [make_ambience(rng, spec["c"], total) for _ in spec["ambience_ref_db"]]
     return evs, ambs
+
+
+# ---- DCASE 2024 metadata (synthesize.py:742-878) -------------------------------------------------------------------------
+class DcaseEmitter:
+    def __init__(self, polar_by_mic):
+        self.coordinates_relative_polar = polar_by_mic  # {mic: (1, 3) array: azimuth deg, elevation deg, distance m}
+
+
+class DcaseEvent:
+    def __init__(self, scene_start, duration, class_id, filename, emitters):
+        self.scene_start = scene_start
+        self.scene_end = scene_start + duration
+        self.class_id = class_id
+        self.filename = filename
+        self.emitters = emitters
+        self.is_moving = len(emitters) > 1
+
+
+class DcaseScene:
+    """The attributes generate_dcase2024_metadata reads from a Scene."""
+
+    def __init__(self, duration, mics, events):
+        import types
+        from collections import OrderedDict
+        self.duration = duration
+        self.state = types.SimpleNamespace(microphones=OrderedDict((m, None) for m in mics))
+        self._events = events
+
+    def get_events(self):
+        return list(self._events)
+
+
+def dcase_static_scene(duration, events, mic="poltest"):
+    """events: [(az, el, dist_m, scene_start, duration, class_id, filename)] — the form of the reference's own
+    expected-table tests (tests/test_dcase_metadata.py:247-352)."""
+    evs = [DcaseEvent(st, du, cls, fn, [DcaseEmitter({mic: np.array([[az, el, dist]], dtype=np.float64)})])
+           for az, el, dist, st, du, cls, fn in events]
+    return DcaseScene(duration, [mic], evs)
+
+
+def dcase_random_scene(seed, duration=60.0, n_events=9, mics=("mic000", "mic001"), moving_fraction=0.4):
+    """Seeded scene with static and moving events on a 0.1 s grid (Scene.add_event rounds nothing, but the metadata
+    function requires starts/ends that land on the frame grid after round(., 1)), repeated files and ties."""
+    rng = np.random.default_rng(seed)
+    files = [f"file{k}.wav" for k in range(max(2, n_events - 2))]
+    evs = []
+    for _ in range(n_events):
+        dur = float(rng.uniform(0.3, 10.0))
+        start = float(rng.uniform(-0.5, duration - 0.2))  # some start before 0 / end after the scene
+        n_em = int(rng.integers(2, 40)) if rng.random() < moving_fraction else 1
+        ems = []
+        for _e in range(n_em):
+            ems.append(DcaseEmitter({m: np.array([[rng.uniform(-180, 180), rng.uniform(-90, 90), rng.uniform(0.2, 9.0)]])
+                                     for m in mics}))
+        fn = files[int(rng.integers(0, len(files)))]
+        evs.append(DcaseEvent(start, dur, int(rng.integers(0, 13)), fn, ems))
+    # exact half-way values exercise round-half-even
+    evs.append(DcaseEvent(1.0, 0.5, 3, "half.wav", [DcaseEmitter({m: np.array([[2.5, -3.5, 0.125]]) for m in mics})]))
+    return DcaseScene(duration, list(mics), evs)
+
+
+DCASE_RANDOM_SEEDS = [101, 102, 103, 104, 105, 106]

@@ -116,10 +116,6 @@ def main():
     np.savez_compressed(os.path.join(HERE, "scenes.npz"), **out)
 
 
-if __name__ == "__main__":
-    main()
-
-
 def make_augment_golden():
     """Fade / Invert / Reverse of the unmodified reference (augmentation.py:1403-1601) -> tests/golden/augment.npz."""
     ref_loader.load_reference_synthesize()
@@ -139,5 +135,22 @@ def make_augment_golden():
     np.savez_compressed(os.path.join(HERE, "augment.npz"), **out)
 
 
+def make_dcase_golden():
+    """Rows of the unmodified reference generate_dcase2024_metadata (synthesize.py:742-878) on the seeded duck-typed
+    scenes of cases.dcase_random_scene -> tests/golden/dcase.npz."""
+    syn = ref_loader.load_reference_synthesize()
+    out = {}
+    for seed in cases.DCASE_RANDOM_SEEDS:
+        scene = cases.dcase_random_scene(seed)
+        res = syn.generate_dcase2024_metadata(scene)
+        for mic, df in res.items():
+            out[f"s{seed}_{mic}"] = df.reset_index(drop=False).to_numpy().astype(np.int64)
+            out[f"s{seed}_{mic}_csv"] = np.frombuffer(df.to_csv(sep=",", encoding="utf-8", header=None).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "dcase.npz"), **out)
+    print("dcase.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    main()
     make_augment_golden()
+    make_dcase_golden()
