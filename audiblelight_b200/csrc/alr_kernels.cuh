@@ -798,36 +798,56 @@ __global__ void k_amb_final(AmbDev* __restrict__ ambs, int n_amb, const float* _
 __global__ void __launch_bounds__(256)
 k_mix(const SceneDev* __restrict__ scenes, const AmbDev* __restrict__ ambs, const MixEv* __restrict__ mevs) {
   const SceneDev& sc = scenes[blockIdx.y];
-  const long long tile0 = (long long)blockIdx.x * 1024;
-  if (tile0 >= sc.T) return;
-  const long long tile1 = min(tile0 + 1024, sc.T);
-  for (int c = 0; c < sc.C; ++c) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long T = sc.T, tile0 = (long long)blockIdx.x * 1024;
+  if (tile0 >= T) return;
+  const int tlen = (int)min(1024LL, T - tile0), tid = threadIdx.x;
+  // The kernel was issue-bound (73 % issue, 54 % DRAM) on 64-bit index arithmetic repeated per channel and sample:
+  // events are now filtered once per group of 4 channels, and one unsigned compare per sample replaces the bounds
+  // checks (rel = sample index inside the event; valid iff 0 <= rel < lim).
+  for (int c0 = 0; c0 < sc.C; c0 += 4) {
+    const int nc = min(4, sc.C - c0);
+    float acc[4][4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[cc][q] = 0.f;
     for (int a = 0; a < sc.n_amb; ++a) {
       const AmbDev& am = ambs[sc.amb0 + a];
-      const float* __restrict__ d = am.data + (long long)c * sc.T;
+      const float scale = am.scale;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const long long tt = tile0 + threadIdx.x + 256 * q;
-        if (tt < tile1) acc[q] = fmaf(am.scale, __ldg(d + tt), acc[q]);
+      for (int cc = 0; cc < 4; ++cc) {
+        if (cc < nc) {
+          const float* __restrict__ d = am.data + (long long)(c0 + cc) * T + tile0 + tid;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (tid + 256 * q < tlen) acc[cc][q] = fmaf(scale, __ldg(d + 256 * q), acc[cc][q]);
+        }
       }
     }
     for (int k = 0; k < sc.nev; ++k) {
       const MixEv& me = mevs[sc.ev0 + k];
-      if (me.end <= tile0 || me.start >= tile1) continue;  // uniform per CTA
-      const float* __restrict__ y = me.y + (long long)c * me.n_out;
+      if (me.end <= tile0 || me.start >= tile0 + tlen) continue;  // uniform per CTA
+      const int base = (int)(tile0 - me.start);                   // in (-1024, end - start)
+      const int lim = (int)min(min(me.end - me.start, (long long)me.n_out), (long long)base + tlen);
+      if (lim <= 0) continue;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const long long tt = tile0 + threadIdx.x + 256 * q;
-        const long long idx = tt - me.start;
-        if (tt < tile1 && tt >= me.start && tt < me.end && idx < me.n_out) acc[q] += __ldg(y + idx);
+      for (int cc = 0; cc < 4; ++cc) {
+        if (cc < nc) {
+          const float* __restrict__ y = me.y + (long long)(c0 + cc) * me.n_out + base + tid;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if ((unsigned)(base + tid + 256 * q) < (unsigned)lim) acc[cc][q] += __ldg(y + 256 * q);
+        }
       }
     }
-    float* __restrict__ out = sc.mix + (long long)c * sc.T;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const long long tt = tile0 + threadIdx.x + 256 * q;
-      if (tt < tile1) out[tt] = acc[q];
+    for (int cc = 0; cc < 4; ++cc) {
+      if (cc < nc) {
+        float* __restrict__ out = sc.mix + (long long)(c0 + cc) * T + tile0 + tid;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (tid + 256 * q < tlen) out[256 * q] = acc[cc][q];
+      }
     }
   }
 }

@@ -842,6 +842,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
   for (int64_t sidx = 0; sidx < n_scenes; ++sidx) {
     const alr_scene& u = scenes[sidx];
     if (u.n_channels < 1 || u.n_samples < 1 || !u.mix) return fail(ALR_ERR_INVALID, "scene %d: bad shape", (int)sidx);
+    if (u.n_samples > 0x7ffff000LL) return fail(ALR_ERR_INVALID, "scene %d: too many samples", (int)sidx);
     if (u.n_ambience < 0 || (u.n_ambience > 0 && (!u.ambience || !u.ambience_ref_db)))
       return fail(ALR_ERR_INVALID, "scene %d: bad ambience list", (int)sidx);
     SceneDev& d = h_scenes[sidx];
