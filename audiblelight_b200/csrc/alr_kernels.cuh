@@ -113,7 +113,10 @@ __device__ __forceinline__ float warp_max(float v) {
 // k_ir_fft: one 64-thread group per RIR partition (event e, IR l, partition k, capsule c).
 // Spectrum slot = hslot0 + (l*K + k)*C + c, i.e. layout [l][k][c][P] so that k_cmac reads the C capsules of one
 // (l,k) contiguously.  Also writes the partition's energy sum(h^2) for normalize_irs.
-__global__ void __launch_bounds__(kCtaThreads)
+#ifndef ALR_IRFFT_MINB
+#define ALR_IRFFT_MINB 1
+#endif
+__global__ void __launch_bounds__(kCtaThreads, ALR_IRFFT_MINB)
 k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, int n_tasks,
          const float2* __restrict__ tw, const float2* __restrict__ zeta, float2* __restrict__ hspec,
          float* __restrict__ hen) {
