@@ -16,7 +16,10 @@
 namespace alr {
 
 constexpr int kCtaThreads = kGroup * kGroupsPerCta;  // 256
-constexpr int kChanGroup = 4;                        // capsules per CMAC thread / CTA
+#ifndef ALR_CMAC_CH
+#define ALR_CMAC_CH 4
+#endif
+constexpr int kChanGroup = ALR_CMAC_CH;              // capsules per k_cmac thread / CTA
 constexpr int kIfftCh = kGroupsPerCta;               // capsules per IFFT CTA (one FFT group each)
 constexpr int kRun = 8;                              // consecutive output blocks per IFFT CTA (tail kept in registers)
 constexpr int kBinCtas = kP / kCtaThreads;           // CMAC CTAs per spectrum (each thread owns one bin)
@@ -113,10 +116,11 @@ __device__ __forceinline__ float warp_max(float v) {
 // k_ir_fft: one 64-thread group per RIR partition (event e, IR l, partition k, capsule c).
 // Spectrum slot = hslot0 + (l*K + k)*C + c, i.e. layout [l][k][c][P] so that k_cmac reads the C capsules of one
 // (l,k) contiguously.  Also writes the partition's energy sum(h^2) for normalize_irs.
-#ifndef ALR_IRFFT_MINB
-#define ALR_IRFFT_MINB 1
-#endif
+#ifdef ALR_IRFFT_MINB  // occupancy experiment, profiles/r01_irfft_occupancy.txt (the default, 64 registers, is fastest)
 __global__ void __launch_bounds__(kCtaThreads, ALR_IRFFT_MINB)
+#else
+__global__ void __launch_bounds__(kCtaThreads)
+#endif
 k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, int n_tasks,
          const float2* __restrict__ tw, const float2* __restrict__ zeta, float2* __restrict__ hspec,
          float* __restrict__ hen) {
@@ -254,8 +258,15 @@ k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix,
 //  * Each H value is used for every output block of the run it contributes to (<= 8 x 4 FFMA per 8 bytes).
 //  * The few source spectra X_l[j] an IR needs are pulled into L1 with prefetch.global.L1 by the producer (i.e.
 //    kStages-1 items early) and read through L1 with the dynamic index j = s + d0 - k.
-constexpr int kG = 8;       // output blocks per CTA
-constexpr int kStages = 5;  // cp.async ring depth: 5 x 4 capsules x 256 threads x 8 B = 40 KB
+constexpr int kG = 8;       // output blocks per CTA (k_cmac_static)
+#ifndef ALR_CMAC_G
+#define ALR_CMAC_G 8
+#endif
+#ifndef ALR_CMAC_STAGES
+#define ALR_CMAC_STAGES 5
+#endif
+constexpr int kGm = ALR_CMAC_G;            // output blocks per CTA (k_cmac); even
+constexpr int kStages = ALR_CMAC_STAGES;  // cp.async ring depth: 5 x 4 capsules x 256 threads x 8 B = 40 KB
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
@@ -290,8 +301,8 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
   const int run = local / ncg;
   const int c0 = cg * kChanGroup;
   const int nc = min(kChanGroup, ev.C - c0);
-  const int b0 = run * kG;
-  const int nb = min(kG, ev.B_valid - b0);
+  const int b0 = run * kGm;
+  const int nb = min(kGm, ev.B_valid - b0);
   const int tid = threadIdx.x;
   const int bin = br * kCtaThreads + tid;
   const int K = ev.K, C = ev.C;
@@ -302,9 +313,9 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
   const float2* __restrict__ hbase = hspec + (ev.hslot0 + c0) * kP + bin;
   float2* const ring_t = &ring[0][0][tid];  // this thread's column: stage stride 4*256, capsule stride 256 elements
 
-  float2 acc[kG][kChanGroup];
+  float2 acc[kGm][kChanGroup];
 #pragma unroll
-  for (int s = 0; s < kG; ++s)
+  for (int s = 0; s < kGm; ++s)
 #pragma unroll
     for (int c = 0; c < kChanGroup; ++c) acc[s][c] = make_float2(0.f, 0.f);
 
@@ -402,7 +413,7 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
       // so the bodies are PAIRS of output blocks (32 FFMA): large enough to stay real basic blocks behind a
       // uniform branch. A block of a pair that is itself out of range gets a zero source value.
 #pragma unroll
-      for (int s = 0; s < kG; s += 2) {
+      for (int s = 0; s < kGm; s += 2) {
         const bool v0 = (unsigned)(s - s_lo) < s_cnt, v1 = (unsigned)(s + 1 - s_lo) < s_cnt;
         if (v0 || v1) {
           float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
@@ -427,7 +438,7 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
     cp_async_wait<0>();
   }
 #pragma unroll
-  for (int s = 0; s < kG; ++s)
+  for (int s = 0; s < kGm; ++s)
     if (s < nb)
 #pragma unroll
       for (int c = 0; c < kChanGroup; ++c)

@@ -199,7 +199,7 @@ int size_event(const alr_event& u, int idx, EvSize& z) {
     z.wband = (int)wb;
   }
   const int ncg = (C + kChanGroup - 1) / kChanGroup;
-  const long long n_cmac = (long long)ceil_div(z.B_valid, kG) * ncg * kBinCtas;
+  const long long n_cmac = (long long)ceil_div(z.B_valid, kGm) * ncg * kBinCtas;
   const long long n_ifft = (long long)((C + kIfftCh - 1) / kIfftCh) * ceil_div(z.B_out, kRun);
   if (z.h > 0x3ffffff0LL || n_cmac > 0x3ffffff0LL || z.xb > 0x3ffffff0LL)
     return fail(ALR_ERR_INVALID, "event %d: too large for 32-bit task indices", idx);
