@@ -623,7 +623,10 @@ k_ifft_ola(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ pref
       m = fmaxf(m, s_max[w]);
       s += s_sum[w];
     }
-    partials[part_base + blockIdx.x] = make_float2(m, s);
+    // slot relative to the EVENT's range: events without IRs (k_tile) own partial slots too, so the chunk-wide CTA
+    // index is not the slot index (found by tests/test_gpu_fuzz.py: every event after a no-IR event got a wrong gain)
+    partials[ev.part0 + local] = make_float2(m, s);
+    (void)part_base;
   }
 }
 

@@ -98,6 +98,16 @@ def _ptr(a) -> int:
     return a.data_ptr() if _is_torch(a) else a.ctypes.data
 
 
+def _require_f32(a, name: str, contiguous: bool = True) -> None:
+    """The C-ABI takes raw float32 pointers: anything else (float64 arrays above all) would be reinterpreted silently."""
+    if a is None:
+        return
+    if "float32" not in str(a.dtype):
+        raise TypeError(f"{name} must be float32, got {a.dtype}")
+    if contiguous and not (a.is_contiguous() if _is_torch(a) else a.flags.c_contiguous):
+        raise ValueError(f"{name} must be C-contiguous")
+
+
 def _strides_elems(a):
     if _is_torch(a):
         return tuple(a.stride())
@@ -160,6 +170,11 @@ class Renderer:
             elif device_mode != mode:
                 raise ValueError("cannot mix host (numpy) and device (torch) buffers in one call")
             C_ = int(e.n_channels)
+            _require_f32(e.audio, "audio")
+            _require_f32(e.irs, "irs", contiguous=False)
+            _require_f32(e.spatial, "spatial")
+            _require_f32(e.dry_out, "dry_out")
+            _require_f32(e.audio_out, "audio_out")
             if e.prerendered:
                 n_out = int(e.spatial.shape[1])
                 a.n_irs = -1
@@ -245,6 +260,7 @@ class Renderer:
                         raise ValueError(
                             f"Scene ambient noise does not match expected shape. "
                             f"Expected {(s.n_channels, s.n_samples)}, but got {tuple(amb.shape)}.")
+                    _require_f32(amb, "ambience")
                     if device_mode is None:
                         device_mode = _is_torch(amb)
                 ptrs = (C.c_void_p * n_amb)(*[_ptr(amb) for amb in s.ambience])
@@ -268,6 +284,7 @@ class Renderer:
                 if ref is None:
                     ref = np.empty(0, dtype=np.float32)
                 s.mix = self._alloc_like(ref, (s.n_channels, s.n_samples))
+            _require_f32(s.mix, "mix")
             b.mix = _ptr(s.mix)
         stats = (AlrEventStats * max(n_ev, 1))()
         return dict(ev=ev_arr, sc=sc_arr, n_ev=n_ev, n_sc=n_sc, stats=stats, keep=keep,

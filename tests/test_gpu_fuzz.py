@@ -1,0 +1,88 @@
+"""Randomised parity (GPU vs the float64 oracle) over ragged shapes: one batched alr_render call holding dozens of
+events of every kind (no IR / static / moving, 1-6 capsules, lengths from 1 sample to a few partitions, IRs longer
+than the audio, negative SNRs, dry audio) and a few scenes mixing them at random offsets with ambience.
+Tolerance: BASELINE.json north_star, max-abs error <= 1e-5 of full scale; timings (slices) bit-exact."""
+import numpy as np
+import pytest
+
+import cases
+import gpu_util
+from gpu_util import TOL
+from audiblelight_b200.renderer import Renderer, SceneJob, event_slice, scene_samples
+from oracle import synth_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_event(rng, sr, c):
+    kind = rng.choice(["none", "static", "moving"], p=[0.1, 0.45, 0.45])
+    lx = int(rng.choice([1, 2, 127, 128, 129, 255, 256, 257, 511, 700, 2047, 2048, 2049, 3333, 4097, 6000]))
+    lh = int(rng.choice([1, 2, 100, 255, 256, 513, 2047, 2048, 2049, 3000, 5000]))
+    if kind == "none":
+        n = 0
+    elif kind == "static":
+        n = 1
+    else:
+        n = int(rng.integers(2, 7))
+        lx = max(lx, 257)  # a moving event needs at least two STFT hops of audio to have frames at all
+    audio = cases.make_audio(rng, lx)
+    irs = cases.make_irs(rng, c, n, lh)
+    snr = float(rng.choice([-12.0, -1.0, 0.5, 5.0, 17.0, 30.0]))
+    spec = dict(sr=sr, snr=snr, ref_db=int(rng.choice([-65, -40, 0])))
+    if n >= 1 and rng.random() < 0.3:
+        spec["ref_ir_channel"] = int(rng.integers(0, c))
+        spec["direct_path_time_ms"] = (float(rng.uniform(0.0, 5.0)), float(rng.uniform(0.5, 30.0)))
+    return spec, audio, irs
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_batch_matches_oracle(seed):
+    rng = np.random.default_rng(9000 + seed)
+    sr = float(rng.choice([8000, 16000, 24000, 44100]))
+    n_scenes = 3
+    scenes, jobs, meta = [], [], []
+    for s in range(n_scenes):
+        c = int(rng.integers(1, 7))
+        duration = float(rng.uniform(0.2, 0.6))
+        total = scene_samples(duration, sr)
+        n_amb = int(rng.integers(0, 3))
+        ambs = [np.ascontiguousarray(cases.make_ambience(rng, c, total), dtype=np.float32) for _ in range(n_amb)]
+        dbs = [float(rng.choice([-65.0, -50.0, -20.0])) for _ in range(n_amb)]
+        scenes.append(SceneJob(n_channels=c, n_samples=total, ambience=ambs, ambience_ref_db=dbs))
+        for _ in range(int(rng.integers(1, 8))):
+            spec, audio, irs = _random_event(rng, sr, c)
+            start = float(rng.uniform(-0.05, duration))
+            j = gpu_util.event_job(spec, audio, irs)
+            j.n_channels = c
+            dur = len(audio) / sr
+            j.scene = s
+            j.scene_start, j.scene_end = event_slice(start, start + dur, sr, total)
+            jobs.append(j)
+            meta.append((s, spec, audio, irs, start, dur))
+    r = Renderer(0)
+    r.render(jobs, scenes)
+    r.close()
+    per_scene = [[] for _ in range(n_scenes)]
+    for j, (s, spec, audio, irs, start, dur) in zip(jobs, meta):
+        n = irs.shape[1]
+        res = orc.render_event(audio, irs.astype(np.float64), spec["snr"], spec["ref_db"], is_moving=n > 1, duration=dur,
+                               sample_rate=sr, ref_ir_channel=spec.get("ref_ir_channel"),
+                               direct_path_time_ms=spec.get("direct_path_time_ms"), literal=False)
+        scale = max(np.abs(res.spatial).max(), 1e-30)
+        err = np.abs(j.spatial - res.spatial).max()
+        # (ref_db = 0 with a high SNR puts the signal far above full scale: the 1e-5 bound then scales with the peak)
+        assert err <= TOL * max(1.0, scale) and err <= 3e-5 * scale + 1e-12, (seed, spec, audio.shape, irs.shape, err, scale)
+        if res.dry is not None:
+            derr = np.abs(j.dry_out - res.dry).max()
+            dscale = max(np.abs(res.dry).max(), 1e-30)
+            assert derr <= TOL * max(1.0, dscale) and derr <= 3e-5 * dscale + 1e-12
+        per_scene[s].append((res.spatial, start, start + dur, j))
+    for s, sc in enumerate(scenes):
+        sp = [p[0] for p in per_scene[s]]
+        # the oracle's mixer takes the channel count from the events; scenes here always hold >= 1 event
+        mix = orc.mix_scene(sc.n_samples / sr, sr, sp, [p[1] for p in per_scene[s]], [p[2] for p in per_scene[s]],
+                            list(zip(sc.ambience, sc.ambience_ref_db)))
+        assert [(p[3].scene_start, p[3].scene_end) for p in per_scene[s]] == mix.slices  # bit-exact timings
+        err = np.abs(sc.mix.astype(np.float64) - mix.scene).max()
+        mscale = max(np.abs(mix.scene).max(), 1e-30)
+        assert err <= TOL * max(1.0, mscale) and err <= 3e-5 * mscale + 1e-12

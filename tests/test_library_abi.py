@@ -3,6 +3,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -42,3 +43,20 @@ def test_no_gpu_fails_loudly():
     from audiblelight_b200.renderer import Renderer
     with pytest.raises(_lib.AlrenderError, match="no CUDA device|no CPU fallback"):
         Renderer(0)
+
+
+def test_pack_rejects_non_float32_buffers():
+    """The binding hands raw pointers to the library: float64 input must fail loudly, not be reinterpreted."""
+    import pytest
+    from audiblelight_b200.renderer import EventJob, Renderer, SceneJob
+    r = Renderer.__new__(Renderer)  # pack() needs no device context
+    ok = EventJob(audio=np.zeros(10, np.float32), irs=np.zeros((2, 1, 5), np.float32), n_channels=2)
+    r.pack([ok], [])
+    with pytest.raises(TypeError, match="audio must be float32"):
+        r.pack([EventJob(audio=np.zeros(10), irs=np.zeros((2, 1, 5), np.float32), n_channels=2)], [])
+    with pytest.raises(TypeError, match="irs must be float32"):
+        r.pack([EventJob(audio=np.zeros(10, np.float32), irs=np.zeros((2, 1, 5)), n_channels=2)], [])
+    with pytest.raises(TypeError, match="ambience must be float32"):
+        r.pack([ok], [SceneJob(n_channels=2, n_samples=20, ambience=[np.zeros((2, 20))], ambience_ref_db=[-65.0])])
+    with pytest.raises(ValueError, match="audio must be C-contiguous"):
+        r.pack([EventJob(audio=np.zeros(20, np.float32)[::2], irs=None, n_channels=2)], [])
