@@ -182,3 +182,69 @@ def test_gpu_normalise_only_and_silent_audio(rnd):
     got = _augment_only(rnd, x, [], normalize=True)
     assert np.abs(got - ao.peak_normalize(x)).max() < 1e-6
     assert np.all(_augment_only(rnd, np.zeros(3000, np.float32), [A.gain_db(6.0)], normalize=True) == 0)   # silent file -> no NaN
+
+
+def _random_chain(rng, sr, n):
+    """(device ops, oracle function) for a random chain of 1-6 linear effects."""
+    ops, fns = [], []
+    for _ in range(int(rng.integers(1, 7))):
+        kind = rng.choice(["gain", "invert", "reverse", "fade", "lowpass", "highpass", "low_shelf", "high_shelf", "peak",
+                           "preemphasis", "deemphasis", "delay"])
+        if kind == "gain":
+            db = float(rng.uniform(-12, 6))
+            ops.append(A.gain_db(db)); fns.append(lambda x, db=db: ao.gain_db(x, db))
+        elif kind == "invert":
+            ops.append(A.invert()); fns.append(ao.invert)
+        elif kind == "reverse":
+            ops.append(A.reverse()); fns.append(ao.reverse)
+        elif kind == "fade":
+            fi, fo = float(rng.uniform(0, 1.2 * n / sr)), float(rng.uniform(0, 1.2 * n / sr))
+            si, so = (A.FADE_SHAPES[int(rng.integers(0, 6))] for _ in range(2))
+            ops.append(A.fade(sr, fi, fo, si, so)); fns.append(lambda x, a=(fi, fo, si, so): ao.fade(x, sr, *a))
+        elif kind in ("lowpass", "highpass"):
+            fc = float(rng.uniform(50.0, 0.45 * sr))
+            b, a = (A.lowpass_coeffs if kind == "lowpass" else A.highpass_coeffs)(sr, fc)
+            ops.append(A.biquad(b, a)); fns.append(lambda x, b=b, a=a: ao.biquad(x, b, a))
+        elif kind in ("low_shelf", "high_shelf", "peak"):
+            fc, g, q = float(rng.uniform(200.0, 0.4 * sr)), float(rng.uniform(-15, 9)), float(rng.uniform(0.3, 2.0))
+            b, a = {"low_shelf": A.low_shelf_coeffs, "high_shelf": A.high_shelf_coeffs, "peak": A.peak_coeffs}[kind](sr, fc, g, q)
+            ops.append(A.biquad(b, a)); fns.append(lambda x, b=b, a=a: ao.biquad(x, b, a))
+        elif kind == "preemphasis":
+            c = float(rng.uniform(0.0, 0.97))
+            ops.append(A.preemphasis(c)); fns.append(lambda x, c=c: ao.preemphasis(x, c))
+        elif kind == "deemphasis":
+            c = float(rng.uniform(0.0, 0.9))
+            ops.append(A.deemphasis(c)); fns.append(lambda x, c=c: ao.deemphasis(x, c))
+        else:
+            d, fb, mix = float(rng.uniform(0.0, 1.5 * n / sr)), float(rng.uniform(0.0, 0.6)), float(rng.uniform(0.0, 1.0))
+            ops.append(A.delay(sr, d, fb, mix)); fns.append(lambda x, a=(d, fb, mix): ao.delay(x, sr, *a))
+
+    def run(x):
+        y = x.astype(np.float64)
+        for f in fns:
+            y = np.asarray(f(y), dtype=np.float64)
+        return y
+    return ops, run
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(8))
+def test_gpu_random_augmentation_chains(rnd, seed):
+    """Several events with random chains and ragged lengths in ONE call (the ops of one level share launches)."""
+    from audiblelight_b200.renderer import EventJob
+    rng = np.random.default_rng(300 + seed)
+    sr = float(rng.choice([8000.0, 24000.0, 44100.0]))
+    jobs, wants = [], []
+    for _ in range(int(rng.integers(2, 9))):
+        n = int(rng.choice([2, 3, 31, 32, 33, 511, 512, 513, 1024, 1500, 5000, 20001]))
+        x = rng.standard_normal(n).astype(np.float32)
+        ops, run = _random_chain(rng, sr, n)
+        norm = bool(rng.random() < 0.5)
+        y = run(x)
+        wants.append(ao.peak_normalize(y) if norm else y)
+        jobs.append(EventJob(audio=x, irs=None, n_channels=1, snr=1.0, ref_db=0.0, aug_ops=ops, normalize_audio=norm,
+                             audio_out=np.zeros(n, np.float32)))
+    rnd.render(jobs)
+    for j, want in zip(jobs, wants):
+        scale = max(1.0, np.abs(want).max())
+        assert np.abs(j.audio_out - want).max() < 5e-5 * scale, (seed, [o.type for o in j.aug_ops], len(want))
