@@ -268,6 +268,33 @@ constexpr int kG = 8;       // output blocks per CTA (k_cmac_static)
 constexpr int kGm = ALR_CMAC_G;            // output blocks per CTA (k_cmac); even
 constexpr int kStages = ALR_CMAC_STAGES;  // cp.async ring depth: 5 x 4 capsules x 256 threads x 8 B = 40 KB
 
+// ---- packed fp32 pairs (Blackwell FFMA2, experiment): `fma.rn.f32x2` does two FMAs per instruction on a 64-bit
+// register pair. A complex multiply-accumulate
+//   acc += x * h   is   acc = fma2({x.re, x.re}, {h.re, h.im}, acc);  acc = fma2({-x.im, x.im}, {h.im, h.re}, acc)
+// i.e. 2 instructions instead of 4, with the same per-component operation order (bit-identical results).
+// Measured (tools/micro/ffma2_bench.cu, profiles/r01_ffma2.txt): plain 3-register FFMA already reaches 120 of the 128
+// FMA/clk/SM on B200, FFMA2 123 — packing saves issue slots, not pipe time. In k_cmac_static the operand packing
+// (MOVs) and the extra live registers (spills at the 128-register cap) made it SLOWER (2.33 -> 2.86 ms), so it is off.
+#ifndef ALR_FFMA2
+#define ALR_FFMA2 0
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -495,11 +522,19 @@ k_cmac_static(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ p
       for (int c = 0; c < kStaticCh; ++c) h[c] = (c < nc) ? __ldg(hbase + k * kstride + (long long)c * kP) : zero;
     }
   };
+#if ALR_FFMA2
+  f32x2 acc[kG][kStaticCh];
+#pragma unroll
+  for (int s = 0; s < kG; ++s)
+#pragma unroll
+    for (int c = 0; c < kStaticCh; ++c) acc[s][c] = 0ull;
+#else
   float2 acc[kG][kStaticCh];
 #pragma unroll
   for (int s = 0; s < kG; ++s)
 #pragma unroll
     for (int c = 0; c < kStaticCh; ++c) acc[s][c] = zero;
+#endif
   float2 W[kG], hA[kStaticCh], hB[kStaticCh];
 #pragma unroll
   for (int s = 0; s < kG; ++s) W[s] = load_x(b0 + s);  // window of partition 0
@@ -519,6 +554,24 @@ k_cmac_static(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ p
         // W[(s - r) & 7] == X[b0 + s - k]; the H request for step k + 1 goes out before this step's arithmetic
         if (r & 1) load_h(k + 1, hA); else load_h(k + 1, hB);
         const float2 (&h)[kStaticCh] = (r & 1) ? hB : hA;
+#if ALR_FFMA2
+        f32x2 hd[kStaticCh], hs[kStaticCh];  // {re, im} and {im, re}
+#pragma unroll
+        for (int c = 0; c < kStaticCh; ++c) {
+          hd[c] = pack2(h[c].x, h[c].y);
+          hs[c] = pack2(h[c].y, h[c].x);
+        }
+#pragma unroll
+        for (int s = 0; s < kG; ++s) {
+          const float2 xv = W[(s - r) & 7];
+          const f32x2 xx = pack2(xv.x, xv.x), xy = pack2(-xv.y, xv.y);
+#pragma unroll
+          for (int c = 0; c < kStaticCh; ++c) {
+            acc[s][c] = fma2(xx, hd[c], acc[s][c]);
+            acc[s][c] = fma2(xy, hs[c], acc[s][c]);
+          }
+        }
+#else
 #pragma unroll
         for (int s = 0; s < kG; ++s) {
           const float2 xv = W[(s - r) & 7];
@@ -530,6 +583,7 @@ k_cmac_static(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ p
             acc[s][c].y = fmaf(xv.y, h[c].x, acc[s][c].y);
           }
         }
+#endif
         // the slot of output 7 of this step becomes output 0 of step k + 1: row b0 - (k + 1), requested during
         // step k - 1; its register is then free for the row of step k + 3
         if (r & 1) {  // k + 1 is even
@@ -547,7 +601,11 @@ k_cmac_static(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ p
     if (s < nb)
 #pragma unroll
       for (int c = 0; c < kStaticCh; ++c)
+#if ALR_FFMA2
+        if (c < nc) yspec[(ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin] = unpack2(acc[s][c]);
+#else
         if (c < nc) yspec[(ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin] = acc[s][c];
+#endif
 }
 
 // k_ifft_ola: one CTA per (event, group of 4 capsules, run of kRun output blocks); group g handles capsule c0+g.
