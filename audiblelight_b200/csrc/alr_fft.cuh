@@ -43,8 +43,36 @@ __device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
+// (bit-identical results; 12 % fewer instructions in the FFT kernels, 1 % of the benchmark step: profiles/r01_ffma2.txt)
+#ifndef ALR_FADD2
+#define ALR_FADD2 1
+#endif
+#if ALR_FADD2
+// complex add / subtract as ONE packed instruction (Blackwell FADD2, add.rn.f32x2 on a 64-bit register pair)
+__device__ __forceinline__ unsigned long long f2_bits(float2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 bits_f2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(r);
+}
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
 // barrier over one FFT group of kGroup threads (named barriers 1..4; 0 stays __syncthreads)
@@ -131,7 +159,10 @@ __device__ __forceinline__ void fft_core(float2 (&v)[16], FftSmem& s, const floa
   // twiddle seeds: issue the table loads first so that their latency hides behind pass A
   const int tq = t & 15;
   constexpr int kB = kP / 256;  // pass-B twiddle exp(-2 pi i tq r / 256) = tw[tq * r * kB]
-  float2 w1 = __ldg(tw + kB * tq), w2 = __ldg(tw + 2 * kB * tq), w4 = __ldg(tw + 4 * kB * tq), w8 = __ldg(tw + 8 * kB * tq);
+  // (the seeds come from the compact copy behind the table, same values as tw[kB * tq << j]: the strided originals cost
+  // 16 L1 wavefronts per warp request, 40 % of the kernel's global-memory wavefronts)
+  static_assert(kB >= 1, "");
+  float2 w1 = __ldg(tw + kP + tq), w2 = __ldg(tw + kP + 16 + tq), w4 = __ldg(tw + kP + 32 + tq), w8 = __ldg(tw + kP + 48 + tq);
   float2 wt = __ldg(tw + t);
   if (INV) {
     w1.y = -w1.y; w2.y = -w2.y; w4.y = -w4.y; w8.y = -w8.y; wt.y = -wt.y;

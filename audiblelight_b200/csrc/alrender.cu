@@ -404,11 +404,15 @@ int prof_mark(alr_context* ctx, cudaStream_t st, int cat) {
   } while (0)
 
 int init_tables(alr_context* ctx) {
-  std::vector<float2> tw(kP);
+  std::vector<float2> tw(kP + 64);
   for (int m = 0; m < kP; ++m) {
     double a = -2.0 * M_PI * (double)m / (double)kP;
     tw[m] = make_float2((float)cos(a), (float)sin(a));
   }
+  // compact copy of the pass-B seeds w^(1,2,4,8) of fft_core: entry kP + 16 j + tq = tw[(kP/256 << j) * tq]. The strided
+  // originals sit in 16 different 128-byte lines per warp request; the copy is one line per request.
+  for (int j = 0; j < 4; ++j)
+    for (int tq = 0; tq < 16; ++tq) tw[kP + 16 * j + tq] = tw[((kP / 256) << j) * tq];
   std::vector<float2> zeta(kGroup);
   for (int t = 0; t < kGroup; ++t) {
     double a = M_PI * (double)t / (double)(2 * kP);
