@@ -19,6 +19,14 @@ constexpr int kCtaThreads = kGroup * kGroupsPerCta;  // 256
 #ifndef ALR_CMAC_CH
 #define ALR_CMAC_CH 4
 #endif
+#ifndef ALR_IR_TASKS
+#define ALR_IR_TASKS 8
+#endif
+#ifndef ALR_X_TASKS
+#define ALR_X_TASKS 4
+#endif
+constexpr int kXTasks = ALR_X_TASKS;                 // source blocks transformed per FFT group of k_x_fft
+constexpr int kIrTasks = ALR_IR_TASKS;               // RIR partitions transformed per FFT group of k_ir_fft
 constexpr int kChanGroup = ALR_CMAC_CH;              // capsules per k_cmac thread / CTA
 constexpr int kIfftCh = kGroupsPerCta;               // capsules per IFFT CTA (one FFT group each)
 constexpr int kRun = 8;                              // consecutive output blocks per IFFT CTA (tail kept in registers)
@@ -116,47 +124,65 @@ __device__ __forceinline__ float warp_max(float v) {
 // k_ir_fft: one 64-thread group per RIR partition (event e, IR l, partition k, capsule c).
 // Spectrum slot = hslot0 + (l*K + k)*C + c, i.e. layout [l][k][c][P] so that k_cmac reads the C capsules of one
 // (l,k) contiguously.  Also writes the partition's energy sum(h^2) for normalize_irs.
-#ifdef ALR_IRFFT_MINB  // occupancy experiment, profiles/r01_irfft_occupancy.txt (the default, 64 registers, is fastest)
-__global__ void __launch_bounds__(kCtaThreads, ALR_IRFFT_MINB)
-#else
-__global__ void __launch_bounds__(kCtaThreads)
+#ifndef ALR_IRFFT_MINB  // occupancy experiment, profiles/r01_irfft_occupancy.txt: 4 CTAs per SM (64 registers) is fastest
+#define ALR_IRFFT_MINB 4
 #endif
+__global__ void __launch_bounds__(kCtaThreads, ALR_IRFFT_MINB)
 k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, int n_tasks,
          const float2* __restrict__ tw, const float2* __restrict__ zeta, float2* __restrict__ hspec,
          float* __restrict__ hen) {
   __shared__ FftSmem sm[kGroupsPerCta];
-  __shared__ float s_red[kGroupsPerCta][kGroup / 32];
+  __shared__ float s_red[kGroupsPerCta][2][kGroup / 32];
   const int g = threadIdx.x / kGroup, t = threadIdx.x % kGroup, bar = 1 + g;
-  const int task = blockIdx.x * kGroupsPerCta + g;
-  if (task >= n_tasks) return;  // whole group leaves together
-  const int e = find_segment(prefix, n_ev, task);
-  const EvDev& ev = evs[e];
-  int local = task - __ldg(prefix + e);
-  const int c = local % ev.C;
-  local /= ev.C;
-  const int k = local % ev.K;
-  const int l = local / ev.K;
-  const float* __restrict__ src = ev.irs + (long long)c * ev.ir_stride_c + (long long)l * ev.ir_stride_n;
-  const int t0 = k * kP;
-  const int lo = max(ev.mask_lo, t0), hi = min(min(ev.mask_hi, ev.Lh), t0 + kP);
+  // Each group transforms kIrTasks consecutive partitions: the event lookup (a chain of ~8 dependent loads) and the
+  // descriptor reads are paid once per group instead of once per transform (consecutive tasks share the event).
+  const int task0 = (blockIdx.x * kGroupsPerCta + g) * kIrTasks;
+  if (task0 >= n_tasks) return;  // whole group leaves together
+  int e = find_segment(prefix, n_ev, task0);
+  int seg_lo = __ldg(prefix + e), seg_hi = __ldg(prefix + e + 1);
   const float2 zt = __ldg(zeta + t);
-  float a[16];
-  float en = 0.f;
+  for (int i = 0; i < kIrTasks; ++i) {
+    const int task = task0 + i;
+    if (task >= n_tasks) break;
+    while (task >= seg_hi) {  // next event (empty segments are skipped)
+      ++e;
+      seg_lo = seg_hi;
+      seg_hi = __ldg(prefix + e + 1);
+    }
+    const EvDev& ev = evs[e];
+    int local = task - seg_lo;
+    const int c = local % ev.C;
+    local /= ev.C;
+    const int k = local % ev.K;
+    const int l = local / ev.K;
+    const float* __restrict__ src = ev.irs + (long long)c * ev.ir_stride_c + (long long)l * ev.ir_stride_n;
+    const int t0 = k * kP;
+    const int lo = max(ev.mask_lo, t0), hi = min(min(ev.mask_hi, ev.Lh), t0 + kP);
+    float a[16];
+    float en = 0.f;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const int n = t0 + t + kGroup * r;
-    a[r] = (n >= lo && n < hi) ? __ldg(src + n) : 0.f;
-    en = fmaf(a[r], a[r], en);
-  }
-  const long long slot = ev.hslot0 + (long long)(l * ev.K + k) * ev.C + c;
-  en = warp_sum(en);
-  if ((t & 31) == 0) s_red[g][t >> 5] = en;
-  fwd_block_to_global(a, zt, sm[g], tw, t, bar, hspec + slot * kP);  // contains group barriers
-  if (t == 0) {
-    float tot = 0.f;
+    for (int r = 0; r < 16; ++r) {
+      const int n = t0 + t + kGroup * r;
+      a[r] = (n >= lo && n < hi) ? __ldg(src + n) : 0.f;
+      en = fmaf(a[r], a[r], en);
+    }
+    const long long slot = ev.hslot0 + (long long)(l * ev.K + k) * ev.C + c;
+    en = warp_sum(en);
+    // The partial sums are double-buffered by task parity: buffer i & 1 is read after this task's transform (>= 4 group
+    // barriers after the writes) and rewritten two tasks later, so the loop needs no barrier of its own (the
+    // transform's trailing barrier protects the exchange buffer). A first version used a single buffer and a named
+    // barrier at the end of the loop body, right behind the thread-0-only block below: about every second run of a
+    // 40-event batch the energies of neighbouring tasks got mixed (per-IR scales off by 15 %; compute-sanitizer's
+    // racecheck saw nothing, the timing changes under the tool). tests/test_gpu_configs.py::
+    // test_many_events_one_call_matches_individual_calls caught it; the mechanism was not pinned down further.
+    if ((t & 31) == 0) s_red[g][i & 1][t >> 5] = en;
+    fwd_block_to_global(a, zt, sm[g], tw, t, bar, hspec + slot * kP);  // contains group barriers, ends with one
+    if (t == 0) {
+      float tot = 0.f;
 #pragma unroll
-    for (int w = 0; w < kGroup / 32; ++w) tot += s_red[g][w];
-    hen[slot] = tot;
+      for (int w = 0; w < kGroup / 32; ++w) tot += s_red[g][i & 1][w];
+      hen[slot] = tot;
+    }
   }
 }
 
@@ -194,56 +220,71 @@ __global__ void k_ir_scale(const EvDev* __restrict__ evs, int n_ev, const int* _
 // x[t] * irscale_l * g_l(t), with g_l(t) = w[q,l] cos^2(pi p/256) + w[q+1,l] sin^2(pi p/256), q = t / 128,
 // p = t % 128: the Hann-smoothed source-side cross-fade that is equivalent to the reference's STFT-domain
 // interpolation (generate_interpolation_matrix + stft window, synthesize.py:120,148-181).
-__global__ void __launch_bounds__(kCtaThreads)
+__global__ void __launch_bounds__(kCtaThreads, 4)
 k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, int n_tasks,
         const IrDev* __restrict__ irs, const float* __restrict__ wband, const float* __restrict__ irscale,
         const float2* __restrict__ tw, const float2* __restrict__ zeta, const float* __restrict__ win,
         float2* __restrict__ xspec) {
   __shared__ FftSmem sm[kGroupsPerCta];
   const int g = threadIdx.x / kGroup, t = threadIdx.x % kGroup, bar = 1 + g;
-  const int task = blockIdx.x * kGroupsPerCta + g;
-  if (task >= n_tasks) return;
-  const int e = find_segment(prefix, n_ev, task);
-  const EvDev& ev = evs[e];
-  const int local = task - __ldg(prefix + e);
-  // IR owning this X slot: largest l with xslot[l] <= local
-  int l = 0;
-  {
-    int lo = 0, hi = ev.N;
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (irs[ev.ir0 + mid].xslot <= local) lo = mid; else hi = mid;
-    }
-    l = lo;
-  }
-  const IrDev ir = irs[ev.ir0 + l];
-  const int j = local - ir.xslot;
-  const int t0 = (ir.xb0 + j) * kP;
-  const float sc = irscale[ev.ir0 + l] * (ev.xnorm ? __ldg(ev.xnorm) : 1.f);
-  const float* __restrict__ x = ev.x;
+  // kXTasks consecutive source blocks per group: the two lookups (event, then IR inside the event: ~15 dependent
+  // loads) are done once and then advanced incrementally
+  const int task0 = (blockIdx.x * kGroupsPerCta + g) * kXTasks;
+  if (task0 >= n_tasks) return;
+  int e = find_segment(prefix, n_ev, task0);
+  int seg_lo = __ldg(prefix + e), seg_hi = __ldg(prefix + e + 1);
+  int l = -1;  // IR index inside the event, -1: search
   const float2 zt = __ldg(zeta + t);
-  // sin^2(pi p / 256) for the in-frame positions of this thread's samples: offset t + kGroup r inside the block, i.e.
-  // p = t (+ 64 for odd r when kGroup == 64)
-  float s_even = 0.f, s_odd = 0.f;
-  if (ev.moving) {
-    s_even = __ldg(win + (t & 127));
-    s_odd = __ldg(win + ((t + 64) & 127));
-  }
-  float a[16];
-#pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const int n = t0 + t + kGroup * r;
-    float v = (n < ev.xlimit) ? __ldg(x + n) : 0.f;
-    float gw = sc;
-    if (ev.moving) {
-      const int q = (t0 >> 7) + ((t + kGroup * r) >> 7) - ir.jmin;  // STFT frame of sample n
-      const float w0 = (q >= 0 && q < ir.nrows) ? __ldg(wband + ir.woff + q) : 0.f;
-      const float w1 = (q + 1 >= 0 && q + 1 < ir.nrows) ? __ldg(wband + ir.woff + q + 1) : 0.f;
-      gw = sc * fmaf(w1 - w0, (kGroup == 64 && (r & 1)) ? s_odd : s_even, w0);  // w0 (1 - s) + w1 s
+  for (int i = 0; i < kXTasks; ++i) {
+    const int task = task0 + i;
+    if (task >= n_tasks) break;
+    while (task >= seg_hi) {
+      ++e;
+      seg_lo = seg_hi;
+      seg_hi = __ldg(prefix + e + 1);
+      l = -1;
     }
-    a[r] = v * gw;
+    const EvDev& ev = evs[e];
+    const int local = task - seg_lo;
+    // IR owning this X slot: largest l with xslot[l] <= local
+    if (l < 0) {
+      int lo = 0, hi = ev.N;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (irs[ev.ir0 + mid].xslot <= local) lo = mid; else hi = mid;
+      }
+      l = lo;
+    } else {
+      while (l + 1 < ev.N && irs[ev.ir0 + l + 1].xslot <= local) ++l;
+    }
+    const IrDev ir = irs[ev.ir0 + l];
+    const int j = local - ir.xslot;
+    const int t0 = (ir.xb0 + j) * kP;
+    const float sc = irscale[ev.ir0 + l] * (ev.xnorm ? __ldg(ev.xnorm) : 1.f);
+    const float* __restrict__ x = ev.x;
+    // sin^2(pi p / 256) for the in-frame positions of this thread's samples: offset t + kGroup r inside the block, i.e.
+    // p = t (+ 64 for odd r when kGroup == 64)
+    float s_even = 0.f, s_odd = 0.f;
+    if (ev.moving) {
+      s_even = __ldg(win + (t & 127));
+      s_odd = __ldg(win + ((t + 64) & 127));
+    }
+    float a[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int n = t0 + t + kGroup * r;
+      float v = (n < ev.xlimit) ? __ldg(x + n) : 0.f;
+      float gw = sc;
+      if (ev.moving) {
+        const int q = (t0 >> 7) + ((t + kGroup * r) >> 7) - ir.jmin;  // STFT frame of sample n
+        const float w0 = (q >= 0 && q < ir.nrows) ? __ldg(wband + ir.woff + q) : 0.f;
+        const float w1 = (q + 1 >= 0 && q + 1 < ir.nrows) ? __ldg(wband + ir.woff + q + 1) : 0.f;
+        gw = sc * fmaf(w1 - w0, (kGroup == 64 && (r & 1)) ? s_odd : s_even, w0);  // w0 (1 - s) + w1 s
+      }
+      a[r] = v * gw;
+    }
+    fwd_block_to_global(a, zt, sm[g], tw, t, bar, xspec + (ev.xslot0 + local) * kP);  // ends with a group barrier
   }
-  fwd_block_to_global(a, zt, sm[g], tw, t, bar, xspec + (ev.xslot0 + local) * kP);
 }
 
 // k_cmac: Y[b,c] = sum over IRs l, source blocks j of l and partitions k with xb0_l + j + k = b of X_l[j] * H_l[k,c].

@@ -1289,7 +1289,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         LAUNCH_CHECK(kCatOther);
       }
       if (n_irfft > 0) {
-        k_ir_fft<<<ceil_div(n_irfft, kGroupsPerCta), kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_irfft),
+        k_ir_fft<<<ceil_div(n_irfft, kGroupsPerCta * kIrTasks), kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_irfft),
                                                                         n_irfft, ctx->d_tw, ctx->d_zeta, d_hspec, d_hen);
         LAUNCH_CHECK(kCatIrFft);
         k_ir_scale<<<ceil_div((long long)n_irs * 32, 128), 128, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_ir), n_irs,
@@ -1297,7 +1297,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         LAUNCH_CHECK(kCatOther);
       }
       if (n_xfft > 0) {
-        k_x_fft<<<ceil_div(n_xfft, kGroupsPerCta), kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_xfft), n_xfft,
+        k_x_fft<<<ceil_div(n_xfft, kGroupsPerCta * kXTasks), kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_xfft), n_xfft,
                                                                        c_irs, c_wband, c_irscale, ctx->d_tw, ctx->d_zeta,
                                                                        ctx->d_win, d_xspec);
         LAUNCH_CHECK(kCatXFft);
