@@ -387,7 +387,19 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
 #pragma unroll
     for (int c = 0; c < kChanGroup; ++c) acc[s][c] = make_float2(0.f, 0.f);
 
-  for (int l0 = lmin; l0 <= lmax; l0 += kMaxHeads) {
+  // Experiment (ALR_CMAC_ZIGZAG=1, off): odd runs walk their (IR, partition) items in DESCENDING order. Neighbouring runs
+  // share the items at the run boundary (each H partition contributes to 3-4 consecutive output blocks: 1.4x re-reads
+  // at a 10 % L2 hit rate); with alternating directions runs r and r+1 reach the shared items at the same end of their
+  // lists. Measured: k_cmac 5.80 -> 6.04 ms per benchmark step: CTAs of neighbouring runs do not stay in step, so the
+  // second read still misses L2, and the descending walk is slower on its own (profiles/r01_cmac_variants.txt).
+#ifndef ALR_CMAC_ZIGZAG
+#define ALR_CMAC_ZIGZAG 0
+#endif
+  const int sgn = (ALR_CMAC_ZIGZAG && (run & 1)) ? -1 : 1;
+  const long long kstep = sgn * kstride;
+  const int n_win = (lmax - lmin + kMaxHeads) / kMaxHeads;
+  for (int wi = 0; wi < n_win; ++wi) {
+    const int l0 = lmin + kMaxHeads * (sgn > 0 ? wi : n_win - 1 - wi);
     const int n_heads = min(kMaxHeads, lmax - l0 + 1);
     __syncthreads();  // previous window fully consumed
     if (tid < n_heads) {
@@ -405,20 +417,21 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
     __syncthreads();
 
     // ---- producer state: next (IR, partition) item whose H values get copied into the ring
-    int ph = -1, pk = 0, pk_hi = -1;
+    int ph = sgn > 0 ? -1 : n_heads, pk = 0, pk_left = 0;  // pk_left: partitions of the current IR still to produce
     const float2* php = hbase;
     bool prod_ok = true;
     auto prod_advance = [&]() {
-      if (++pk <= pk_hi) {
-        php += kstride;
+      if (--pk_left > 0) {
+        pk += sgn;
+        php += kstep;
         return;
       }
-      while (++ph < n_heads) {
+      while ((unsigned)(ph += sgn) < (unsigned)n_heads) {
         const CmacHead h = heads[ph];
         if (h.k_lo <= h.k_hi) {
-          pk = h.k_lo;
-          pk_hi = h.k_hi;
-          php = hbase + h.hoff;
+          pk = sgn > 0 ? h.k_lo : h.k_hi;
+          pk_left = h.k_hi - h.k_lo + 1;
+          php = hbase + h.hoff + (long long)(pk - h.k_lo) * kstride;
           // entering an IR: pull the source spectra it needs into L1 (kStages-1 items before they are used)
           const int j_lo = max(0, h.d0 - h.k_hi), j_hi = min(h.xnb - 1, h.d0 + nb - 1 - h.k_lo);
           const float2* xp = xbase + h.xoff;
@@ -439,21 +452,20 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
       cp_async_commit();  // (possibly empty) group: keeps the group count in step with the item count
     };
     // ---- consumer state
-    int ch = -1, ck = 0, ck_hi = -1, cjb = 0, cxnb = 0;
+    int ch = sgn > 0 ? -1 : n_heads, ck_left = 0, cjb = 0, cxnb = 0;
     const float2* cxq = xbase;  // &X_l[jb][bin]: X of output s is cxq[s * kP]
     bool cons_ok = true;
     auto cons_advance = [&]() {
-      if (++ck <= ck_hi) {
-        --cjb;
-        cxq -= kP;
+      if (--ck_left > 0) {  // next partition k + sgn: source block j = s + d0 - k moves the other way
+        cjb -= sgn;
+        cxq -= sgn * kP;
         return;
       }
-      while (++ch < n_heads) {
+      while ((unsigned)(ch += sgn) < (unsigned)n_heads) {
         const CmacHead h = heads[ch];
         if (h.k_lo <= h.k_hi) {
-          ck = h.k_lo;
-          ck_hi = h.k_hi;
-          cjb = h.d0 - h.k_lo;
+          ck_left = h.k_hi - h.k_lo + 1;
+          cjb = h.d0 - (sgn > 0 ? h.k_lo : h.k_hi);
           cxnb = h.xnb;
           cxq = xbase + h.xoff + (long long)cjb * kP;
           return;
