@@ -53,6 +53,7 @@ struct EvDev {
   int parent;            // dry events: stats index of the parent event, else -1
   int stat;              // index into the stats array
   int part0, nparts;     // range of reduction partials written by k_ifft_ola
+  int gain_from;         // k_apply_gain scales samples [gain_from, n_out) of every channel; [0, gain_from) is left to k_mix
   int dry_channel, dry_low, dry_high;
   const float* xnorm;    // optional scalar the dry audio is multiplied with (peak normalisation), or NULL
   double snr, ref_db;
@@ -92,7 +93,8 @@ struct AmbDev {
 };
 
 struct MixEv {
-  const float* y;
+  float* y;
+  const float* gain;  // non-NULL: y still holds the un-scaled render; k_mix applies (and stores) the event gain
   long long start, end;
   int n_out;
   int pad;
@@ -828,6 +830,15 @@ __global__ void k_apply_gain(const EvDev* __restrict__ evs, const float* __restr
   float* __restrict__ y = ev.y;
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ev.gain_from > 0) {  // the head of every channel is scaled by k_mix while it is mixed (one pass over y less)
+    const int tail = ev.n_out - ev.gain_from;
+    if (tail <= 0) return;
+    for (long long q = i; q < (long long)ev.C * tail; q += stride) {
+      const long long c = q / tail, n = ev.gain_from + q % tail;
+      y[c * ev.n_out + n] *= gain;
+    }
+    return;
+  }
   if ((reinterpret_cast<uintptr_t>(y) & 15u) == 0) {
     float4* y4 = reinterpret_cast<float4*>(y);
     const long long n4 = total >> 2;
@@ -958,6 +969,28 @@ k_mix(const SceneDev* __restrict__ scenes, const AmbDev* __restrict__ ambs, cons
       const int base = (int)(tile0 - me.start);                   // in (-1024, end - start)
       const int lim = (int)min(min(me.end - me.start, (long long)me.n_out), (long long)base + tlen);
       if (lim <= 0) continue;
+      if (me.gain) {
+        // fused k_apply_gain: the stored event audio becomes gain * y (rounded to float32 once, as before), and that
+        // rounded value is what the mix adds
+        const float g = __ldg(me.gain);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          if (cc < nc) {
+            float* __restrict__ y = me.y + (long long)(c0 + cc) * me.n_out + base + tid;
+            float v[4];  // all loads first: the stores below must not serialise them
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = ((unsigned)(base + tid + 256 * q) < (unsigned)lim) ? y[256 * q] : 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if ((unsigned)(base + tid + 256 * q) < (unsigned)lim) {
+                v[q] *= g;
+                y[256 * q] = v[q];
+                acc[cc][q] += v[q];
+              }
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         if (cc < nc) {

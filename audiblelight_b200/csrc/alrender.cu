@@ -839,6 +839,8 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     }
   // ---- scene / ambience / mix descriptors (independent of the event plans) ------------------------------------------
   std::vector<SceneDev> h_scenes(n_scenes);
+  std::vector<int> mev_event;                 // per mix entry: the event whose gain k_mix applies, or -1
+  std::vector<int> gain_from(n_events, 0);    // per event: first sample k_apply_gain still has to scale
   bool any_pcm = false;
   std::vector<AmbDev> h_ambs;
   std::vector<MixEv> h_mevs;
@@ -882,6 +884,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       off += count[sidx];
     }
     h_mevs.resize(off);
+    mev_event.assign(off, -1);
     for (int64_t i = 0; i < n_events; ++i) {  // call order == the reference's dict order
       const alr_event& u = events[i];
       if (u.scene < 0 || u.scene_end <= u.scene_start) continue;
@@ -891,6 +894,14 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       SceneDev& sd = h_scenes[u.scene];
       MixEv& m = h_mevs[sd.ev0 + sd.nev++];
       m.y = u.spatial;
+      m.gain = nullptr;
+      // Device buffers: the event gain is applied by k_mix while it reads the event anyway (k_apply_gain then only
+      // scales what the scene does not cover). With host buffers the event audio is downloaded right after its chunk,
+      // before the mix, so it is scaled per chunk as usual.
+      if (!host_mode && u.n_irs != -1 && u.gain_mode != ALR_GAIN_NONE) {
+        mev_event[sd.ev0 + sd.nev - 1] = (int)i;
+        gain_from[i] = (int)std::min<int64_t>(u.scene_end - u.scene_start, u.n_out);
+      }
       m.start = u.scene_start;
       m.end = u.scene_end;
       m.n_out = (int)u.n_out;
@@ -941,6 +952,8 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
   float* d_hen = (float*)(mbase + mo_hen);
   float2* d_parts = (float2*)(mbase + mo_parts);
   float* d_gain = (float*)(mbase + mo_gain);
+  for (size_t k = 0; k < h_mevs.size(); ++k)  // phase-0 events own gain slots [0, n_events) in call order
+    if (mev_event[k] >= 0) h_mevs[k].gain = d_gain + mev_event[k];
   EvStat* d_stats = (EvStat*)(mbase + mo_stats);
   float* d_ambparts = (float*)(mbase + mo_amb);
   CUDA_TRY(cudaMemsetAsync(d_stats, 0, std::max<size_t>(n_events, 1) * sizeof(EvStat), st));
@@ -1230,6 +1243,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
           const int parent_ev = ph == 0 ? ei : dry_parent[ei];
           d.xnorm = (d_xnorm && ev_norm_idx[parent_ev] >= 0) ? d_xnorm + ev_norm_idx[parent_ev] : nullptr;
         }
+        if (ph == 0) d.gain_from = gain_from[ei];
         if (ph == 1) {
           d.gain_mode = kGainDry;
           d.parent = dry_parent[ei];
