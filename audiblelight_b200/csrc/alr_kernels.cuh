@@ -667,7 +667,10 @@ k_cmac_static(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ p
 // Inverse transform of Y[b]; the real part of element e is sample e of the block, the imaginary part its overlap
 // tail (sample P + e), which the SAME thread adds to block b+1 — the tail never leaves registers. Scale 1/P,
 // truncate to n_valid, zero fill up to n_out (pad_or_truncate_audio, utils.py:667), reduce max|y| and sum|y|.
-__global__ void __launch_bounds__(kCtaThreads)
+#ifndef ALR_IFFT_MINB
+#define ALR_IFFT_MINB 3  // 80 registers, 3 CTAs per SM: 2.11 ms per benchmark step (2 CTAs at 127 registers 2.20, 4 CTAs at 64 with spills 2.30)
+#endif
+__global__ void __launch_bounds__(kCtaThreads, ALR_IFFT_MINB)
 k_ifft_ola(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const float2* __restrict__ tw,
            const float2* __restrict__ zeta, const float2* __restrict__ yspec, float2* __restrict__ partials,
            int part_base) {
