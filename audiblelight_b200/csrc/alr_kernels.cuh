@@ -1,15 +1,19 @@
 // alr_kernels.cuh — device descriptors and kernels of the renderer (sm_100a).
 //
 // Pipeline per chunk of events (each kernel cites the reference code it replaces):
-//   k_ir_fft      RIR partitions -> packed half spectra (+ per-partition energy)      synthesize.py:103,298,425
+//   k_ir_fft      RIR partitions -> block spectra (+ per-partition energy)            synthesize.py:103,298,425
 //   k_ir_scale    per-IR normalisation scalar a_l                                      synthesize.py:404-428,560
 //   k_x_fft       source blocks x cross-fade weight g_l -> spectra                     synthesize.py:148-181,299
-//   k_cmac        Y[b,c] = sum_{l,j,k: xb0_l+j+k=b} X_l[j] * H_l[k,c]                  synthesize.py:184-252 / :103
+//   k_cmac        Y[b,c] = sum_{l,j,k: xb0_l+j+k=b} X_l[j] * H_l[k,c]  (moving events)  synthesize.py:184-252
+//   k_cmac_static the same contraction for one-IR events (regular block FIR)           synthesize.py:103
 //   k_ifft_ola    inverse FFT + overlap-add + truncation + max|y|, sum|y| partials     synthesize.py:255-274,590
 //   k_event_gain  apply_snr / db_to_multiplier scalars                                 synthesize.py:40-68,594-599
-//   k_apply_gain  y *= gain                                                            synthesize.py:594,599
+//   k_apply_gain  y *= gain (device buffers: only what k_mix does not cover)           synthesize.py:594,599
 //   k_amb_*       mean|ambience| -> scale                                              synthesize.py:350-352
 //   k_mix         scene = sum ambience*scale + sum events in [start,end)               synthesize.py:328-378
+//   k_pcm16       (C,T) float mix -> (T,C) PCM_16 as Scene.generate writes it         core.py:1840-1847
+// Before the chunk loop (f1): k_aug_pointwise, k_iir_pass / k_iir_combine, k_peak_partial / k_peak_final apply the
+// linear event augmentations and the peak normalisation of Event.load_audio           event.py:530-536
 #pragma once
 #include "alr_fft.cuh"
 
@@ -123,7 +127,8 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_ir_fft: one 64-thread group per RIR partition (event e, IR l, partition k, capsule c).
+// k_ir_fft: one group of kGroup threads per RIR partition (event e, IR l, partition k, capsule c), kIrTasks
+// consecutive partitions per group.
 // Spectrum slot = hslot0 + (l*K + k)*C + c, i.e. layout [l][k][c][P] so that k_cmac reads the C capsules of one
 // (l,k) contiguously.  Also writes the partition's energy sum(h^2) for normalize_irs.
 #ifndef ALR_IRFFT_MINB  // occupancy experiment, profiles/r01_irfft_occupancy.txt: 4 CTAs per SM (64 registers) is fastest
