@@ -135,12 +135,18 @@ def generate_scenes(scenes: Sequence, output_dir: Optional[Union[str, Path]] = N
                     metadata_json: bool = True, metadata_dcase: bool = True,
                     audio_fnames: Optional[Sequence[Union[str, Path]]] = None,
                     metadata_fnames: Optional[Sequence[Union[str, Path]]] = None,
-                    batch_scenes: int = 16, device: int = -1, keep_audio: bool = False) -> List[Dict[str, List[Path]]]:
+                    batch_scenes: int = 16, device: int = -1, keep_audio: bool = False,
+                    pipeline: bool = True) -> List[Dict[str, List[Path]]]:
     """`scene.generate(output_dir, audio, metadata_json, metadata_dcase, audio_fname, metadata_fname)` for every scene
     of the list, `batch_scenes` scenes per GPU call. File names default to audio_out_<i> / metadata_out_<i>.
     `keep_audio=True` also leaves `scene.audio` / `event.spatial_audio` populated as `Scene.generate` would
-    (more device->host traffic). Returns the paths written, per scene."""
+    (more device->host traffic). With `pipeline=True` batch i+1 is prepared and rendered (second context, worker
+    thread; the library call releases the GIL) while the files of batch i are written. Returns the paths written,
+    per scene."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from . import synthesize as _syn
+    from .renderer import Renderer
     n = len(scenes)
     out_dir = Path(output_dir) if output_dir is not None else Path.cwd()
     if not out_dir.is_dir():
@@ -150,18 +156,24 @@ def generate_scenes(scenes: Sequence, output_dir: Optional[Union[str, Path]] = N
     if len(audio_fnames) != n or len(metadata_fnames) != n:
         raise ValueError("need one audio / metadata file name per scene")
     written: List[Dict[str, List[Path]]] = [dict(audio=[], json=[], csv=[]) for _ in range(n)]
-    for b0 in range(0, n, max(1, int(batch_scenes))):
-        batch = list(scenes[b0:b0 + max(1, int(batch_scenes))])
-        if audio:
-            pcm = _syn.render_scenes(batch, ignore_cache=True, device=device, store_padded=keep_audio, pcm16=True,
-                                     keep_event_audio=keep_audio, keep_mix=keep_audio)
-            for k, scene in enumerate(batch):
+    step = max(1, int(batch_scenes))
+    starts = list(range(0, n, step))
+
+    def render(b0, renderer):
+        batch = list(scenes[b0:b0 + step])
+        if not audio:
+            return batch, None
+        return batch, _syn.render_scenes(batch, ignore_cache=True, device=device, store_padded=keep_audio, pcm16=True,
+                                         keep_event_audio=keep_audio, keep_mix=keep_audio, renderer=renderer)
+
+    def write(b0, batch, pcm):
+        for k, scene in enumerate(batch):
+            if pcm is not None:
                 base = (out_dir / audio_fnames[b0 + k]).with_suffix("")
                 for mic, data in pcm[k].items():
                     p = _with_mic(base, mic, ".wav")
                     write_wav_pcm16(p, data, int(scene.sample_rate))
                     written[b0 + k]["audio"].append(p)
-        for k, scene in enumerate(batch):
             base = (out_dir / metadata_fnames[b0 + k]).with_suffix("")
             if metadata_json:
                 p = base.with_suffix(".json")
@@ -174,4 +186,21 @@ def generate_scenes(scenes: Sequence, output_dir: Optional[Union[str, Path]] = N
                     with open(p, "w", encoding="utf-8", newline="") as f:
                         f.write(dcase_csv(rows))
                     written[b0 + k]["csv"].append(p)
+
+    if not pipeline or not audio or len(starts) < 2:
+        for b0 in starts:
+            write(b0, *render(b0, None))
+        return written
+    contexts = [Renderer(device), Renderer(device)]  # one per batch in flight
+    try:
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(render, starts[0], contexts[0])
+            for i, b0 in enumerate(starts):
+                batch, pcm = pending.result()
+                if i + 1 < len(starts):
+                    pending = pool.submit(render, starts[i + 1], contexts[(i + 1) & 1])
+                write(b0, batch, pcm)
+    finally:
+        for c in contexts:
+            c.close()
     return written

@@ -373,7 +373,8 @@ def generate_scene_audio_from_events(scene) -> None:
 
 # ---- batch entry: many scenes, render + mix in one GPU call ----------------------------------------------------------------
 def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1, store_padded: bool = True,
-                  pcm16: bool = False, keep_event_audio: bool = True, keep_mix: bool = True):
+                  pcm16: bool = False, keep_event_audio: bool = True, keep_mix: bool = True,
+                  renderer: Optional[Renderer] = None):
     """Renders and mixes a whole batch of Scene objects with one `alr_render` call (events are rendered and mixed
     on the device without a host round trip). Equivalent to calling `render_audio_for_all_scene_events(scene,
     ignore_cache)` and `generate_scene_audio_from_events(scene)` on every scene.
@@ -381,7 +382,8 @@ def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1,
     Dataset generation (audiblelight_b200.dataset) only needs the mix as the 16-bit PCM that `Scene.generate` writes:
     `pcm16=True` also returns, per scene, `{mic_alias: (T, C) int16}` packed on the device; `keep_event_audio=False`
     leaves `event.spatial_audio` (and the padded copies) unset and `keep_mix=False` leaves `scene.audio` unset, so
-    that neither is copied back from the GPU."""
+    that neither is copied back from the GPU. `renderer` selects an explicit context (one per concurrent caller; the
+    default is the per-device singleton)."""
     if not keep_mix and not pcm16:
         raise ValueError("keep_mix=False needs pcm16=True")
     if not keep_event_audio:
@@ -414,7 +416,7 @@ def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1,
             all_scenes.append(sjob)
             book.append((scene, mic_alias, sjob, mic_jobs, placements))
     start = time()
-    get_renderer(device).render(all_jobs, all_scenes)
+    (renderer if renderer is not None else get_renderer(device)).render(all_jobs, all_scenes)
     packed = {id(scene): OrderedDict() for scene in scenes}
     for scene, mic_alias, sjob, mic_jobs, placements in book:
         for j, (event, s0, s1) in zip(mic_jobs, placements):

@@ -231,6 +231,20 @@ def test_gpu_generate_scenes_writes_the_dataset(tmp_path):
         rows = dataset.dcase2024_rows(ref_scene)
         for p in written[i]["csv"]:
             assert open(p, newline="").read() == dataset.dcase_csv(rows[p.stem.split("_")[-1]])
+    # the pipelined driver (default; here 3 scenes in batches of 2 and of 1) writes the same bytes as the sequential one
+    for bs in (1, 2):
+        seq_dir = tmp_path / f"seq{bs}"
+        seq_dir.mkdir()
+        again = [_scene(cases.SCENE_CASES[n], idx=i, mics=("mic000", "mic001") if i == 0 else ("mic000",))
+                 for i, n in enumerate(names)]
+        w2 = dataset.generate_scenes(again, seq_dir, batch_scenes=bs, pipeline=(bs == 1),
+                                     audio_fnames=[f"mix_{i}.wav" for i in range(len(scenes))],
+                                     metadata_fnames=[f"meta_{i}" for i in range(len(scenes))])
+        for a, b in zip(written, w2):
+            for kind in ("audio", "json", "csv"):
+                assert [p.name for p in a[kind]] == [p.name for p in b[kind]]
+                for pa, pb in zip(a[kind], b[kind]):
+                    assert open(pa, "rb").read() == open(pb, "rb").read()
     # keep_audio=True behaves like Scene.generate: results stay on the objects
     dataset.generate_scenes(scenes[:1], tmp_path, keep_audio=True, metadata_json=False, metadata_dcase=False)
     assert scenes[0].audio["mic001"].dtype == np.float32 and "mic000" in next(iter(scenes[0].events.values())).spatial_audio
