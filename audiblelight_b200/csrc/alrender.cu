@@ -440,6 +440,21 @@ extern "C" {
 int alr_version(void) { return ALR_VERSION; }
 const char* alr_last_error(void) { return g_err.c_str(); }
 int alr_partition_size(void) { return kP; }
+int alr_pinned_alloc(alr_context* ctx, size_t bytes, void** out) {
+  if (!ctx || !out || bytes == 0) return fail(ALR_ERR_INVALID, "alr_pinned_alloc: bad argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ALR_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  return ALR_OK;
+}
+void alr_pinned_free(alr_context* ctx, void* p) {
+  if (!ctx || !p) return;
+  cudaSetDevice(ctx->device);
+  cudaFreeHost(p);
+}
 int alr_struct_size(int which) {
   switch (which) {
     case 0: return (int)sizeof(alr_event);

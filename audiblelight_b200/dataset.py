@@ -146,7 +146,6 @@ def generate_scenes(scenes: Sequence, output_dir: Optional[Union[str, Path]] = N
     from concurrent.futures import ThreadPoolExecutor
 
     from . import synthesize as _syn
-    from .renderer import Renderer
     n = len(scenes)
     out_dir = Path(output_dir) if output_dir is not None else Path.cwd()
     if not out_dir.is_dir():
@@ -164,7 +163,8 @@ def generate_scenes(scenes: Sequence, output_dir: Optional[Union[str, Path]] = N
         if not audio:
             return batch, None
         return batch, _syn.render_scenes(batch, ignore_cache=True, device=device, store_padded=keep_audio, pcm16=True,
-                                         keep_event_audio=keep_audio, keep_mix=keep_audio, renderer=renderer)
+                                         keep_event_audio=keep_audio, keep_mix=keep_audio, renderer=renderer,
+                                         pinned=True)  # the PCM arrays are written to disk before the pool is reused
 
     def write(b0, batch, pcm):
         for k, scene in enumerate(batch):
@@ -191,16 +191,13 @@ def generate_scenes(scenes: Sequence, output_dir: Optional[Union[str, Path]] = N
         for b0 in starts:
             write(b0, *render(b0, None))
         return written
-    contexts = [Renderer(device), Renderer(device)]  # one per batch in flight
-    try:
-        with ThreadPoolExecutor(max_workers=1) as pool:
-            pending = pool.submit(render, starts[0], contexts[0])
-            for i, b0 in enumerate(starts):
-                batch, pcm = pending.result()
-                if i + 1 < len(starts):
-                    pending = pool.submit(render, starts[i + 1], contexts[(i + 1) & 1])
-                write(b0, batch, pcm)
-    finally:
-        for c in contexts:
-            c.close()
+    # one persistent context per batch in flight (their workspaces and pinned pools stay warm between calls)
+    contexts = [_syn.get_renderer(device, 0), _syn.get_renderer(device, 1)]
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        pending = pool.submit(render, starts[0], contexts[0])
+        for i, b0 in enumerate(starts):
+            batch, pcm = pending.result()
+            if i + 1 < len(starts):
+                pending = pool.submit(render, starts[i + 1], contexts[(i + 1) & 1])
+            write(b0, batch, pcm)
     return written

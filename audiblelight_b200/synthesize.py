@@ -58,13 +58,14 @@ def _load_raw_audio(event) -> np.ndarray:
     return audio_raw
 
 
-def get_renderer(device: int = -1) -> Renderer:
-    """Per-process, per-device renderer context (alr_create is done once)."""
+def get_renderer(device: int = -1, slot: int = 0) -> Renderer:
+    """Per-process, per-device renderer context (alr_create is done once). `slot` > 0 gives further persistent
+    contexts of the same device for callers that keep several batches in flight (audiblelight_b200.dataset)."""
     with _lock:
-        r = _renderers.get(device)
+        r = _renderers.get((device, slot))
         if r is None:
             r = Renderer(device)
-            _renderers[device] = r
+            _renderers[(device, slot)] = r
         return r
 
 
@@ -102,8 +103,43 @@ def _check_stft_geometry(fft_size, win_size, hop_size) -> None:
             f"got {fft_size}/{win_size}/{hop_size}")
 
 
-def _as_f32(a) -> np.ndarray:
-    return np.ascontiguousarray(a, dtype=np.float32)
+_CONVERT_POOL = None
+
+
+def _as_f32(a, pool=None) -> np.ndarray:
+    """C-contiguous float32 copy (no copy if it already is one). The reference's backends deliver float64 RIRs
+    (worldstate.py:2210-2212): for a batch of scenes this conversion is the largest host cost of the drop-in, so
+    big arrays are converted in slices by a small thread pool (numpy releases the GIL while it copies). With `pool`
+    (a renderer's PinnedPool) the result lives in page-locked memory, which the library uploads at the full PCIe rate;
+    such arrays are only valid until the pool is recycled."""
+    a = np.asarray(a)
+    if pool is not None and a.ndim > 0 and a.size >= (1 << 14):
+        out = pool.take(a.shape)
+        if a.size < (1 << 21):
+            np.copyto(out, a, casting="same_kind")
+            return out
+    else:
+        if a.dtype == np.float32 and a.flags.c_contiguous:
+            return a
+        if a.ndim == 0 or a.size < (1 << 21):
+            return np.ascontiguousarray(a, dtype=np.float32)
+        out = np.empty(a.shape, dtype=np.float32)
+    global _CONVERT_POOL
+    if _CONVERT_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        _CONVERT_POOL = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
+    axis = int(np.argmax(a.shape))
+    n = a.shape[axis]
+    parts = min(8, n)
+    bounds = [n * k // parts for k in range(parts + 1)]
+
+    def conv(k):
+        sl = [slice(None)] * a.ndim
+        sl[axis] = slice(bounds[k], bounds[k + 1])
+        np.copyto(out[tuple(sl)], a[tuple(sl)], casting="same_kind")
+    list(_CONVERT_POOL.map(conv, range(parts)))
+    return out
 
 
 # ---- raw convolutions ------------------------------------------------------------------------------------------------
@@ -142,7 +178,7 @@ def time_variant_convolution(irs: np.ndarray, event, fft_size=FFT_SIZE, win_size
 
 
 # ---- event rendering ----------------------------------------------------------------------------------------------------
-def _event_job(event, irs: np.ndarray, ref_db, ignore_cache: bool) -> EventJob:
+def _event_job(event, irs: np.ndarray, ref_db, ignore_cache: bool, pool=None) -> EventJob:
     """Everything render_event_audio does on the host before the arithmetic (synthesize.py:544-587)."""
     n_ch, n_emitters, n_ir_samples = irs.shape
     ops = None
@@ -155,17 +191,17 @@ def _event_job(event, irs: np.ndarray, ref_db, ignore_cache: bool) -> EventJob:
         audio = _load_raw_audio(event)
         _valid_audio(audio)
         n_audio = audio.shape[0]
-        job = EventJob(audio=_as_f32(audio), n_channels=n_ch, snr=float(event.snr), ref_db=float(ref_db), n_out=n_audio,
+        job = EventJob(audio=_as_f32(audio, pool), n_channels=n_ch, snr=float(event.snr), ref_db=float(ref_db), n_out=n_audio,
                        aug_ops=ops, normalize_audio=True, audio_out=np.empty(n_audio, dtype=np.float32))
     else:
         audio = event.load_audio(ignore_cache=ignore_cache, normalize=True)
         _valid_audio(audio)
         n_audio = audio.shape[0]
-        job = EventJob(audio=_as_f32(audio), n_channels=n_ch, snr=float(event.snr), ref_db=float(ref_db), n_out=n_audio)
+        job = EventJob(audio=_as_f32(audio, pool), n_channels=n_ch, snr=float(event.snr), ref_db=float(ref_db), n_out=n_audio)
     if n_emitters == 1:
         if event.is_moving:
             raise ValueError("Moving Event has only one emitter!")
-        job.irs = _as_f32(irs)
+        job.irs = _as_f32(irs, pool)
     elif n_emitters == 0:
         logger.warning(
             f"No IRs were found for Event with alias {event.alias}. Audio is being tiled along the "
@@ -177,7 +213,7 @@ def _event_job(event, irs: np.ndarray, ref_db, ignore_cache: bool) -> EventJob:
             raise ValueError("Expected a moving event!")
         if len(event) != n_emitters:
             raise ValueError(f"Event has {len(event)} emitters but {n_emitters} IRs were given")
-        job.irs = _as_f32(irs)
+        job.irs = _as_f32(irs, pool)
         job.ir_frames, job.n_frames = moving_frames(event.duration, event.sample_rate, len(event), n_audio)
     # dry / direct-path audio (compute_dry_audio, synthesize.py:432-504)
     ref_ch = getattr(event, "ref_ir_channel", None)
@@ -260,7 +296,7 @@ def validate_scene(scene) -> None:
         )
 
 
-def _scene_event_jobs(scene, ignore_cache: bool):
+def _scene_event_jobs(scene, ignore_cache: bool, pool=None):
     """(mic, event) jobs of one scene in the reference's loop order (synthesize.py:653-675), honouring the cache."""
     if ignore_cache:
         scene.state.simulate()
@@ -278,7 +314,7 @@ def _scene_event_jobs(scene, ignore_cache: bool):
             n = len(event)
             event_irs = mic_ir[:, emitter_counter:n + emitter_counter, :]
             if not (mic_alias in event.spatial_audio.keys() and not ignore_cache):
-                jobs.append((mic_alias, event, _event_job(event, np.asarray(event_irs), scene.ref_db, ignore_cache)))
+                jobs.append((mic_alias, event, _event_job(event, np.asarray(event_irs), scene.ref_db, ignore_cache, pool)))
             emitter_counter += n
     return jobs
 
@@ -299,7 +335,7 @@ def _is_ambience(obj) -> bool:
     return hasattr(obj, "load_ambience") and hasattr(obj, "ref_db")
 
 
-def _mix_jobs_for_mic(scene, mic_alias: str, scene_index: int, prerendered: bool, event_jobs=None):
+def _mix_jobs_for_mic(scene, mic_alias: str, scene_index: int, prerendered: bool, event_jobs=None, pool=None):
     """SceneJob + per-event placement for one microphone (synthesize.py:327-378)."""
     channels = max(ev.spatial_audio[mic_alias].shape[0] for ev in scene.events.values()) if prerendered else \
         max(j.n_channels for j in event_jobs)
@@ -315,7 +351,7 @@ def _mix_jobs_for_mic(scene, mic_alias: str, scene_index: int, prerendered: bool
                     f"Scene ambient noise does not match expected shape. "
                     f"Expected {(channels, total)}, but got {noise.shape}."
                 )
-            ambs.append(_as_f32(noise))
+            ambs.append(_as_f32(noise, pool))
             dbs.append(float(ambience.ref_db))
     sjob = SceneJob(n_channels=channels, n_samples=total, ambience=ambs, ambience_ref_db=dbs)
     placements = []
@@ -374,7 +410,7 @@ def generate_scene_audio_from_events(scene) -> None:
 # ---- batch entry: many scenes, render + mix in one GPU call ----------------------------------------------------------------
 def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1, store_padded: bool = True,
                   pcm16: bool = False, keep_event_audio: bool = True, keep_mix: bool = True,
-                  renderer: Optional[Renderer] = None):
+                  renderer: Optional[Renderer] = None, pinned: bool = False):
     """Renders and mixes a whole batch of Scene objects with one `alr_render` call (events are rendered and mixed
     on the device without a host round trip). Equivalent to calling `render_audio_for_all_scene_events(scene,
     ignore_cache)` and `generate_scene_audio_from_events(scene)` on every scene.
@@ -383,7 +419,13 @@ def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1,
     `pcm16=True` also returns, per scene, `{mic_alias: (T, C) int16}` packed on the device; `keep_event_audio=False`
     leaves `event.spatial_audio` (and the padded copies) unset and `keep_mix=False` leaves `scene.audio` unset, so
     that neither is copied back from the GPU. `renderer` selects an explicit context (one per concurrent caller; the
-    default is the per-device singleton)."""
+    default is the per-device singleton). `pinned=True` stages the converted inputs and the PCM output in the
+    renderer's page-locked pool: faster transfers, but the returned PCM arrays are only valid until the next call on
+    the same renderer."""
+    rnd = renderer if renderer is not None else get_renderer(device)
+    pool = rnd.pool if pinned else None
+    if pool is not None:
+        pool.recycle()
     if not keep_mix and not pcm16:
         raise ValueError("keep_mix=False needs pcm16=True")
     if not keep_event_audio:
@@ -392,7 +434,7 @@ def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1,
     all_scenes: List[SceneJob] = []
     book = []
     for scene in scenes:
-        ev_jobs = _scene_event_jobs(scene, ignore_cache)
+        ev_jobs = _scene_event_jobs(scene, ignore_cache, pool)
         by_key = {(m, id(e)): j for m, e, j in ev_jobs}
         for mic_alias in scene.state.microphones.keys():
             mic_jobs = []
@@ -402,7 +444,7 @@ def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1,
                     sp = event.spatial_audio[mic_alias]
                     j = EventJob(spatial=_as_f32(sp), n_channels=sp.shape[0], prerendered=True)
                 mic_jobs.append(j)
-            sjob, placements = _mix_jobs_for_mic(scene, mic_alias, len(all_scenes), False, mic_jobs)
+            sjob, placements = _mix_jobs_for_mic(scene, mic_alias, len(all_scenes), False, mic_jobs, pool)
             for j, (event, s0, s1) in zip(mic_jobs, placements):
                 j.scene, j.scene_start, j.scene_end = len(all_scenes), s0, s1
                 if j.n_channels != sjob.n_channels and s1 > s0:
@@ -410,13 +452,14 @@ def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1,
                 if not keep_event_audio and not j.prerendered and j.dry is None:
                     j.keep_spatial = False
             if pcm16:
-                sjob.pcm16 = np.empty((sjob.n_samples, sjob.n_channels), dtype=np.int16)
+                sjob.pcm16 = (pool.take((sjob.n_samples, sjob.n_channels), np.int16) if pool is not None else
+                              np.empty((sjob.n_samples, sjob.n_channels), dtype=np.int16))
                 sjob.keep_mix = keep_mix
             all_jobs += mic_jobs
             all_scenes.append(sjob)
             book.append((scene, mic_alias, sjob, mic_jobs, placements))
     start = time()
-    (renderer if renderer is not None else get_renderer(device)).render(all_jobs, all_scenes)
+    rnd.render(all_jobs, all_scenes)
     packed = {id(scene): OrderedDict() for scene in scenes}
     for scene, mic_alias, sjob, mic_jobs, placements in book:
         for j, (event, s0, s1) in zip(mic_jobs, placements):

@@ -212,6 +212,12 @@ int alr_get_profile(alr_context* ctx, alr_profile* out);
  * packed half spectra (partition complex values per block; bin 0 holds (Re X[0], Re X[partition])).
  * Inverse: packed spectra -> 2*partition real samples per block, scaled by 1/(2*partition). */
 int alr_partition_size(void);
+
+/* Page-locked host memory for the buffers of ALR_MEM_HOST calls (cudaHostAlloc / cudaFreeHost). Optional: any host
+ * pointer works, pinned ones are copied at the full PCIe rate and asynchronously. The reference keeps its arrays in
+ * ordinary numpy memory; the Python host layer converts the float64 RIRs to float32 straight into such blocks. */
+int alr_pinned_alloc(alr_context* ctx, size_t bytes, void** out);
+void alr_pinned_free(alr_context* ctx, void* p);
 int alr_debug_rfft(alr_context* ctx, const float* in, int64_t n_blocks, int64_t in_stride, int32_t n_valid,
                    float* spec_out, void* stream);
 int alr_debug_irfft(alr_context* ctx, const float* spec_in, int64_t n_blocks, float* out, void* stream);
