@@ -321,10 +321,12 @@ def _scene_event_jobs(scene, ignore_cache: bool, pool=None):
 
 def render_audio_for_all_scene_events(scene, ignore_cache: Optional[bool] = False) -> None:
     """synthesize.py:613-677 — all (microphone, event) renders of the scene, as ONE batched GPU call."""
-    jobs = _scene_event_jobs(scene, bool(ignore_cache))
+    rnd = get_renderer()
+    rnd.pool.recycle()  # inputs are staged in page-locked memory for the duration of this call only
+    jobs = _scene_event_jobs(scene, bool(ignore_cache), rnd.pool)
     start = time()
     if jobs:
-        get_renderer().render([j for _, _, j in jobs])
+        rnd.render([j for _, _, j in jobs])
         for mic_alias, event, job in jobs:
             _store_event_result(event, job, mic_alias)
     logger.info(f"Rendered scene audio in {(time() - start):.2f} seconds!")
