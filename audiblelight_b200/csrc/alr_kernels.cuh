@@ -33,7 +33,10 @@ constexpr int kXTasks = ALR_X_TASKS;                 // source blocks transforme
 constexpr int kIrTasks = ALR_IR_TASKS;               // RIR partitions transformed per FFT group of k_ir_fft
 constexpr int kChanGroup = ALR_CMAC_CH;              // capsules per k_cmac thread / CTA
 constexpr int kIfftCh = kGroupsPerCta;               // capsules per IFFT CTA (one FFT group each)
-constexpr int kRun = 8;                              // consecutive output blocks per IFFT CTA (tail kept in registers)
+#ifndef ALR_IFFT_RUN
+#define ALR_IFFT_RUN 8
+#endif
+constexpr int kRun = ALR_IFFT_RUN;                              // consecutive output blocks per IFFT CTA (tail kept in registers)
 constexpr int kBinCtas = kP / kCtaThreads;           // CMAC CTAs per spectrum (each thread owns one bin)
 
 enum { kGainEvent = 0, kGainNone = 1, kGainDry = 2, kGainPass = 3 };  // Pass: already rendered, only mixed
