@@ -99,3 +99,25 @@ def test_python_layer_shape_errors(rnd):
         rnd.render([_good()], [SceneJob(n_channels=2, n_samples=100, ambience=[np.zeros((2, 99), np.float32)],
                                         ambience_ref_db=[-65.0])])
     rnd.render([], [])  # an empty call is a no-op
+
+
+def test_ambience_only_scene_and_event_outside_any_scene(rnd):
+    """C-ABI corner cases the reference never reaches (it refuses scenes without events): a scene that holds only
+    ambience layers, next to an event that is rendered but not mixed anywhere."""
+    from oracle import synth_oracle as orc
+    rng = np.random.default_rng(5)
+    amb = [np.ascontiguousarray(cases.make_ambience(rng, 3, 5000), dtype=np.float32) for _ in range(2)]
+    sc = SceneJob(n_channels=3, n_samples=5000, ambience=amb, ambience_ref_db=[-40.0, -55.0])
+    ev = _good(seed=3)
+    rnd.render([ev], [sc])
+    want = np.zeros((3, 5000), np.float32)
+    for a, db in zip(amb, (-40.0, -55.0)):
+        want += (orc.db_to_multiplier(db, np.mean(np.abs(a))) * a).astype(np.float32)
+    assert np.abs(sc.mix - want).max() < 1e-6 * np.abs(want).max()
+    alone = _good(seed=3)
+    rnd.render([alone])
+    assert np.array_equal(ev.spatial, alone.spatial)
+    # no ambience, no events: the mix is silence
+    empty = SceneJob(n_channels=2, n_samples=1000, mix=np.ones((2, 1000), np.float32))
+    rnd.render([], [empty])
+    assert not empty.mix.any()
