@@ -1135,87 +1135,99 @@ __device__ __forceinline__ void iir_coeffs(const AugDev& o, float& b0, float& b1
     b0 = o.p[0]; b1 = o.p[1]; b2 = o.p[2]; a1 = o.p[3]; a2 = o.p[4];
   }
 }
-// One thread per chunk streams its samples in 32-sample register tiles: eight independent 16-byte loads per tile (the
-// next tile is requested before the current one is filtered), so ~1000 loads are in flight per CTA and every
-// 128-byte line is consumed by the thread that fetched it. (The first version walked memory sample by sample with a
-// 2 KB stride between lanes and thrashed L1: 3.9 ms per benchmark step; a shared-memory transposing version with
-// only 4 loads in flight per warp still took 1.2 ms.)
+// One thread per 512-sample chunk runs the recurrence; the samples travel through shared memory so that every global
+// access is a coalesced 128-byte row: a warp owns 32 chunks and, per 32-sample step, issues 32 independent row loads
+// (one per chunk, all in flight together), transposes them through a padded 32 x 33 tile, filters its own row and
+// writes the rows back the same way. History of this kernel on the benchmark step (both passes): 3.9 ms walking memory
+// sample by sample at a 2 KB lane stride; 1.2 ms with a transposing tile but 4 loads in flight; 0.54 ms with
+// per-thread 16-byte loads (each warp request still touched 32 lines: L1TEX wavefront bound); this version is bound
+// by the recurrence itself.
 constexpr int kIirCta = 128, kIirSub = 32;
-
-__device__ __forceinline__ void iir_load_tile(const float* __restrict__ src, int n, int n1, bool vec, float (&v)[kIirSub]) {
-  if (vec && n + kIirSub <= n1) {
-#pragma unroll
-    for (int q = 0; q < kIirSub / 4; ++q) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(src + n) + q);
-      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < kIirSub; ++j) v[j] = (n + j < n1) ? __ldg(src + n + j) : 0.f;
-  }
-}
 
 template <bool WRITE>
 __global__ void __launch_bounds__(kIirCta)
 k_iir_pass(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix, int n_ops, int n_chunks,
            float2* __restrict__ zs) {
+  __shared__ float tile[kIirCta / 32][32][33];
+  __shared__ const float* s_src[kIirCta];
+  __shared__ float* s_dst[kIirCta];
+  __shared__ int s_n0[kIirCta], s_n1[kIirCta];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row0 = warp * 32;
   const int c = blockIdx.x * kIirCta + threadIdx.x;
-  if (c >= n_chunks) return;
-  const int oi = find_segment(chunk_prefix, n_ops, c);
-  const AugDev& o = ops[oi];
-  float b0, b1, b2, a1, a2;
-  iir_coeffs(o, b0, b1, b2, a1, a2);
-  const int n0 = (c - chunk_prefix[oi]) * kIirChunk, n1 = min(n0 + kIirChunk, o.L);
-  const float* __restrict__ src = o.src;
-  float* __restrict__ dst = o.dst;
-  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+  const bool live = c < n_chunks;
+  float b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f;
+  int n0 = 0, n1 = 0;
+  const float* src = nullptr;
+  float* dst = nullptr;
   float s1 = 0.f, s2 = 0.f, corr = 0.f, cpow = 1.f, coef = 0.f;
   bool deemph = false;
-  if (WRITE) {
-    s1 = zs[c].x;
-    s2 = zs[c].y;
-    // librosa.effects.deemphasis subtracts ((2 - coef) x0 - x1) / (3 - coef) * coef^n afterwards
-    if (o.type == kAugDeemph && o.L > 1) {
-      deemph = true;
-      coef = o.p[0];
-      corr = ((2.f - coef) * src[0] - src[1]) / (3.f - coef);
-      cpow = powf(coef, (float)n0);
+  if (live) {
+    const int oi = find_segment(chunk_prefix, n_ops, c);
+    const AugDev& o = ops[oi];
+    iir_coeffs(o, b0, b1, b2, a1, a2);
+    n0 = (c - chunk_prefix[oi]) * kIirChunk;
+    n1 = min(n0 + kIirChunk, o.L);
+    src = o.src;
+    dst = o.dst;
+    if (WRITE) {
+      s1 = zs[c].x;
+      s2 = zs[c].y;
+      // librosa.effects.deemphasis subtracts ((2 - coef) x0 - x1) / (3 - coef) * coef^n afterwards
+      if (o.type == kAugDeemph && o.L > 1) {
+        deemph = true;
+        coef = o.p[0];
+        corr = ((2.f - coef) * src[0] - src[1]) / (3.f - coef);
+        cpow = powf(coef, (float)n0);
+      }
     }
   }
-  float cur[kIirSub], nxt[kIirSub];
-  iir_load_tile(src, n0, n1, vec, cur);
-  for (int n = n0; n < n1; n += kIirSub) {
-    if (n + kIirSub < n1) iir_load_tile(src, n + kIirSub, n1, vec, nxt);
+  s_src[threadIdx.x] = src;
+  s_dst[threadIdx.x] = dst;
+  s_n0[threadIdx.x] = n0;
+  s_n1[threadIdx.x] = n1;
+  __syncwarp();
+  float (*T)[33] = tile[warp];
+  for (int sub = 0; sub < kIirChunk / kIirSub; ++sub) {
+    const int off = sub * kIirSub;
+    if (__ballot_sync(0xffffffffu, n0 + off < n1) == 0u) break;  // every chunk of this warp is finished
+    float v[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const int n = s_n0[row0 + r] + off + lane;
+      v[r] = (n < s_n1[row0 + r]) ? __ldg(s_src[row0 + r] + n) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) T[r][lane] = v[r];
+    __syncwarp();
+    const int cnt = min(kIirSub, n1 - n0 - off);  // samples of this thread's chunk in the tile (may be <= 0)
 #pragma unroll
     for (int j = 0; j < kIirSub; ++j) {
-      const float x = cur[j];
-      const float y = fmaf(b0, x, s1);
-      s1 = fmaf(b1, x, fmaf(-a1, y, s2));
-      s2 = fmaf(b2, x, -a2 * y);
-      if (WRITE) {
-        if (deemph) {
-          cur[j] = y - corr * cpow;
-          cpow *= coef;
-        } else {
-          cur[j] = y;
+      if (j < cnt) {
+        const float x = T[lane][j];
+        const float y = fmaf(b0, x, s1);
+        s1 = fmaf(b1, x, fmaf(-a1, y, s2));
+        s2 = fmaf(b2, x, -a2 * y);
+        if (WRITE) {
+          if (deemph) {
+            T[lane][j] = y - corr * cpow;
+            cpow *= coef;
+          } else {
+            T[lane][j] = y;
+          }
         }
       }
     }
+    __syncwarp();
     if (WRITE) {
-      if (vec && n + kIirSub <= n1) {
 #pragma unroll
-        for (int q = 0; q < kIirSub / 4; ++q)
-          reinterpret_cast<float4*>(dst + n)[q] = make_float4(cur[4 * q], cur[4 * q + 1], cur[4 * q + 2], cur[4 * q + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < kIirSub; ++j)
-          if (n + j < n1) dst[n + j] = cur[j];
+      for (int r = 0; r < 32; ++r) {
+        const int n = s_n0[row0 + r] + off + lane;
+        if (n < s_n1[row0 + r]) s_dst[row0 + r][n] = T[r][lane];
       }
+      __syncwarp();
     }
-#pragma unroll
-    for (int j = 0; j < kIirSub; ++j) cur[j] = nxt[j];
   }
-  if (!WRITE) zs[c] = make_float2(s1, s2);
+  if (!WRITE && live) zs[c] = make_float2(s1, s2);
 }
 
 // One WARP per op: lanes fetch 32 zero-state results at once (one coalesced request instead of 32 dependent
