@@ -98,9 +98,18 @@ def _ptr(a) -> int:
     return a.data_ptr() if _is_torch(a) else a.ctypes.data
 
 
+_NP_F32 = np.dtype(np.float32)
+
+
 def _require_f32(a, name: str, contiguous: bool = True) -> None:
     """The C-ABI takes raw float32 pointers: anything else (float64 arrays above all) would be reinterpreted silently."""
     if a is None:
+        return
+    if isinstance(a, np.ndarray):  # (fast path: this runs for every buffer of every event)
+        if a.dtype != _NP_F32:
+            raise TypeError(f"{name} must be float32, got {a.dtype}")
+        if contiguous and not a.flags.c_contiguous:
+            raise ValueError(f"{name} must be C-contiguous")
         return
     if "float32" not in str(a.dtype):
         raise TypeError(f"{name} must be float32, got {a.dtype}")
