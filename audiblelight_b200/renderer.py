@@ -95,8 +95,6 @@ def _is_torch(a) -> bool:
 def _ptr(a) -> int:
     if a is None:
         return 0
-    if isinstance(a, np.ndarray):
-        return a.__array_interface__["data"][0]  # (a.ctypes.data builds a helper object on every call)
     return a.data_ptr() if _is_torch(a) else a.ctypes.data
 
 
