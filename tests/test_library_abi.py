@@ -60,3 +60,51 @@ def test_pack_rejects_non_float32_buffers():
         r.pack([ok], [SceneJob(n_channels=2, n_samples=20, ambience=[np.zeros((2, 20))], ambience_ref_db=[-65.0])])
     with pytest.raises(ValueError, match="audio must be C-contiguous"):
         r.pack([EventJob(audio=np.zeros(20, np.float32)[::2], irs=None, n_channels=2)], [])
+
+
+def test_pinned_pool_reuses_blocks_best_fit():
+    """PinnedPool (host staging for the drop-in): blocks are recycled by best fit, so batches whose arrays differ a
+    little in size do not allocate again (cudaHostAlloc per batch was slower than pageable copies)."""
+    from audiblelight_b200.renderer import PinnedPool
+
+    class FakeLib:  # stands in for libalrender's alr_pinned_alloc / alr_pinned_free
+        def __init__(self):
+            self.allocs, self.frees, self.keep = 0, 0, []
+
+        def alr_pinned_alloc(self, h, nbytes, out):
+            buf = (C.c_byte * nbytes)()
+            self.keep.append(buf)
+            out._obj.value = C.addressof(buf)
+            self.allocs += 1
+            return 0
+
+        def alr_pinned_free(self, h, p):
+            self.frees += 1
+
+    lib = FakeLib()
+    pool = PinnedPool(lib, None)
+    rng = np.random.default_rng(0)
+    seen = []
+    for it in range(6):
+        pool.recycle()
+        arrs = [pool.take((4, int(rng.integers(21, 101)), 2400)) for _ in range(12)]
+        for k, a in enumerate(arrs):
+            assert a.dtype == np.float32 and a.flags.c_contiguous
+            a[...] = k  # blocks handed out in one round must not overlap
+        assert all((a == k).all() for k, a in enumerate(arrs))
+        seen.append(lib.allocs)
+    assert seen[-1] == seen[2] <= 2 * 12  # steady state: no new allocations
+    pcm = pool.take((1000, 4), np.int16)
+    assert pcm.dtype == np.int16 and pcm.shape == (1000, 4)
+    pool.close()
+    assert lib.frees == lib.allocs
+
+
+def test_pooled_float32_conversion_matches_numpy():
+    import audiblelight_b200.synthesize as syn
+    a = np.random.default_rng(1).standard_normal((4, 50, 12000))  # float64, above the threading threshold
+    view = a[:, 7:40, :]                                             # non-contiguous slice, as the drop-in gets them
+    out = syn._as_f32(view)
+    assert out.dtype == np.float32 and out.flags.c_contiguous and np.array_equal(out, view.astype(np.float32))
+    small = np.arange(10, dtype=np.float32)
+    assert syn._as_f32(small) is small
