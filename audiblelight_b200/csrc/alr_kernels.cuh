@@ -230,7 +230,10 @@ __global__ void k_ir_scale(const EvDev* __restrict__ evs, int n_ev, const int* _
 // x[t] * irscale_l * g_l(t), with g_l(t) = w[q,l] cos^2(pi p/256) + w[q+1,l] sin^2(pi p/256), q = t / 128,
 // p = t % 128: the Hann-smoothed source-side cross-fade that is equivalent to the reference's STFT-domain
 // interpolation (generate_interpolation_matrix + stft window, synthesize.py:120,148-181).
-__global__ void __launch_bounds__(kCtaThreads, 4)
+#ifndef ALR_XFFT_MINB
+#define ALR_XFFT_MINB 4
+#endif
+__global__ void __launch_bounds__(kCtaThreads, ALR_XFFT_MINB)
 k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, int n_tasks,
         const IrDev* __restrict__ irs, const float* __restrict__ wband, const float* __restrict__ irscale,
         const float2* __restrict__ tw, const float2* __restrict__ zeta, const float* __restrict__ win,
