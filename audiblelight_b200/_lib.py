@@ -45,7 +45,7 @@ class AlrEventStats(C.Structure):
 
 class AlrProfile(C.Structure):
     _fields_ = [("ms_total", C.c_double), ("ms_ir_fft", C.c_double), ("ms_x_fft", C.c_double),
-                ("ms_cmac", C.c_double), ("ms_cmac_static", C.c_double), ("ms_ifft", C.c_double), ("ms_mix", C.c_double), ("ms_other", C.c_double), ("ms_host_plan", C.c_double),
+                ("ms_cmac", C.c_double), ("ms_cmac_static", C.c_double), ("ms_ifft", C.c_double), ("ms_mix", C.c_double), ("ms_other", C.c_double), ("ms_fused", C.c_double), ("ms_host_plan", C.c_double),
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("workspace_bytes", C.c_int64), ("n_chunks", C.c_int64)]
 

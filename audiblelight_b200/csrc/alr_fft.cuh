@@ -148,14 +148,18 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
 __device__ __forceinline__ constexpr int perm8(int k) { return 2 * (k & 3) + (k >> 2); }
 
 // P-point complex FFT by one group of kGroup = P/16 threads; Stockham autosort, radix 16 x 16 x kR3.
-//   in : v[r] = element (t + kGroup r), r = 0..15                              (t = thread index in the group)
-//   out: o[m][k] = spectrum element (t + kGroup m) + 256 k, m < kM3, k < kR3    (natural order, un-normalised)
-// tw[m] = exp(-2*pi*i*m/P), m < P.  The caller must have a group_sync between any earlier use of `s` by other
-// threads and this call; on return the group may still be reading `s` (last-pass gather), so the caller needs a
-// group_sync before the next transform scatters into `s`.
-template <bool INV>
-__device__ __forceinline__ void fft_core(float2 (&v)[16], FftSmem& s, const float2* __restrict__ tw, int t, int bar,
-                                         float2 (&o)[kM3][kR3]) {
+//   in : v[q][r] = element (t + kGroup r) of transform q, r = 0..15                 (t = thread index in the group)
+//   out: o[q][m][k] = spectrum element (t + kGroup m) + 256 k, m < kM3, k < kR3      (natural order, un-normalised)
+// tw[m] = exp(-2*pi*i*m/P), m < P.  NT independent transforms (exchange buffers s[0..NT)) are carried through the
+// passes TOGETHER: they share the barriers and every twiddle product, and give the scheduler NT independent
+// instruction streams per thread — the persistent kernel (k_mov_fused) runs at 2 CTAs per SM and uses NT = 2 to get
+// the latency hiding the stand-alone FFT kernels get from 4 CTAs per SM.
+// The caller must have a group_sync between any earlier use of `s` by other threads and this call; on return the
+// group may still be reading `s` (last-pass gather), so the caller needs a group_sync before the next transform
+// scatters into `s`.
+template <bool INV, int NT>
+__device__ __forceinline__ void fft_core_n(float2 (&v)[NT][16], FftSmem* __restrict__ s, const float2* __restrict__ tw,
+                                           int t, int bar, float2 (&o)[NT][kM3][kR3]) {
   // twiddle seeds: issue the table loads first so that their latency hides behind pass A
   const int tq = t & 15;
   constexpr int kB = kP / 256;  // pass-B twiddle exp(-2 pi i tq r / 256) = tw[tq * r * kB]
@@ -168,12 +172,17 @@ __device__ __forceinline__ void fft_core(float2 (&v)[16], FftSmem& s, const floa
     w1.y = -w1.y; w2.y = -w2.y; w4.y = -w4.y; w8.y = -w8.y; wt.y = -wt.y;
   }
   // ---- pass A: radix 16, Ns = 1, no twiddles; scatter to 16*t + k
-  dft16<INV>(v);
 #pragma unroll
-  for (int k = 0; k < 16; ++k) s.d[padi(16 * t + k)] = v[perm16(k)];
+  for (int q = 0; q < NT; ++q) {
+    dft16<INV>(v[q]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s[q].d[padi(16 * t + k)] = v[q][perm16(k)];
+  }
   group_sync(bar);
 #pragma unroll
-  for (int r = 0; r < 16; ++r) v[r] = s.d[padi(t + kGroup * r)];
+  for (int q = 0; q < NT; ++q)
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[q][r] = s[q].d[padi(t + kGroup * r)];
   group_sync(bar);
   // ---- pass B: radix 16, Ns = 16; twiddle exp(-2 pi i (t%16) r / 256) = w1^r, built from w1, w2, w4, w8
   {
@@ -181,24 +190,33 @@ __device__ __forceinline__ void fft_core(float2 (&v)[16], FftSmem& s, const floa
                  w12 = cmul(w4, w8);
     const float2 w7 = cmul(w3, w4), w11 = cmul(w3, w8), w13 = cmul(w5, w8), w14 = cmul(w6, w8);
     const float2 w15 = cmul(w7, w8);
-    v[1] = cmul(v[1], w1);   v[2] = cmul(v[2], w2);   v[3] = cmul(v[3], w3);   v[4] = cmul(v[4], w4);
-    v[5] = cmul(v[5], w5);   v[6] = cmul(v[6], w6);   v[7] = cmul(v[7], w7);   v[8] = cmul(v[8], w8);
-    v[9] = cmul(v[9], w9);   v[10] = cmul(v[10], w10); v[11] = cmul(v[11], w11); v[12] = cmul(v[12], w12);
-    v[13] = cmul(v[13], w13); v[14] = cmul(v[14], w14); v[15] = cmul(v[15], w15);
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+      float2 (&u)[16] = v[q];
+      u[1] = cmul(u[1], w1);   u[2] = cmul(u[2], w2);   u[3] = cmul(u[3], w3);   u[4] = cmul(u[4], w4);
+      u[5] = cmul(u[5], w5);   u[6] = cmul(u[6], w6);   u[7] = cmul(u[7], w7);   u[8] = cmul(u[8], w8);
+      u[9] = cmul(u[9], w9);   u[10] = cmul(u[10], w10); u[11] = cmul(u[11], w11); u[12] = cmul(u[12], w12);
+      u[13] = cmul(u[13], w13); u[14] = cmul(u[14], w14); u[15] = cmul(u[15], w15);
+    }
   }
-  dft16<INV>(v);
   const int base = (t >> 4) * 256 + tq;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) s.d[padi(base + 16 * k)] = v[perm16(k)];
+  for (int q = 0; q < NT; ++q) {
+    dft16<INV>(v[q]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s[q].d[padi(base + 16 * k)] = v[q][perm16(k)];
+  }
   group_sync(bar);
   // ---- pass C: radix kR3, Ns = 256; butterfly j = t + kGroup m; twiddle exp(-2 pi i j r / P) = (wt * c_m)^r,
   //      c_m = exp(-2 pi i kGroup m / P) = exp(-i pi m / 8)
 #pragma unroll
-  for (int m = 0; m < kM3; ++m) {
-    const int j = t + kGroup * m;
+  for (int q = 0; q < NT; ++q)
 #pragma unroll
-    for (int r = 0; r < kR3; ++r) o[m][r] = s.d[padi(j + 256 * r)];
-  }
+    for (int m = 0; m < kM3; ++m) {
+      const int j = t + kGroup * m;
+#pragma unroll
+      for (int r = 0; r < kR3; ++r) o[q][m][r] = s[q].d[padi(j + 256 * r)];
+    }
 #pragma unroll
   for (int m = 0; m < kM3; ++m) {
     const float cr[4] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
@@ -207,40 +225,57 @@ __device__ __forceinline__ void fft_core(float2 (&v)[16], FftSmem& s, const floa
     const float2 u1 = (m == 0) ? wt : cmul(wt, cm);
     const float2 u2 = cmul(u1, u1);
     const float2 u3 = cmul(u2, u1);
-    o[m][1] = cmul(o[m][1], u1);
-    o[m][2] = cmul(o[m][2], u2);
-    o[m][3] = cmul(o[m][3], u3);
     if constexpr (kR3 == 16) {
       const float2 u4 = cmul(u2, u2), u8 = cmul(u4, u4);
       const float2 u5 = cmul(u4, u1), u6 = cmul(u4, u2), u7 = cmul(u4, u3);
-      o[m][4] = cmul(o[m][4], u4);   o[m][5] = cmul(o[m][5], u5);   o[m][6] = cmul(o[m][6], u6);
-      o[m][7] = cmul(o[m][7], u7);   o[m][8] = cmul(o[m][8], u8);   o[m][9] = cmul(o[m][9], cmul(u8, u1));
-      o[m][10] = cmul(o[m][10], cmul(u8, u2)); o[m][11] = cmul(o[m][11], cmul(u8, u3));
-      o[m][12] = cmul(o[m][12], cmul(u8, u4)); o[m][13] = cmul(o[m][13], cmul(u8, u5));
-      o[m][14] = cmul(o[m][14], cmul(u8, u6)); o[m][15] = cmul(o[m][15], cmul(u8, u7));
-      dft16<INV>(o[m]);
-      float2 tmp[16];
+      const float2 u9 = cmul(u8, u1), u10 = cmul(u8, u2), u11 = cmul(u8, u3), u12 = cmul(u8, u4), u13 = cmul(u8, u5),
+                   u14 = cmul(u8, u6), u15 = cmul(u8, u7);
 #pragma unroll
-      for (int k = 0; k < 16; ++k) tmp[k] = o[m][perm16(k)];
+      for (int q = 0; q < NT; ++q) {
+        float2 (&x)[kR3] = o[q][m];
+        x[1] = cmul(x[1], u1);   x[2] = cmul(x[2], u2);   x[3] = cmul(x[3], u3);   x[4] = cmul(x[4], u4);
+        x[5] = cmul(x[5], u5);   x[6] = cmul(x[6], u6);   x[7] = cmul(x[7], u7);   x[8] = cmul(x[8], u8);
+        x[9] = cmul(x[9], u9);   x[10] = cmul(x[10], u10); x[11] = cmul(x[11], u11); x[12] = cmul(x[12], u12);
+        x[13] = cmul(x[13], u13); x[14] = cmul(x[14], u14); x[15] = cmul(x[15], u15);
+        dft16<INV>(x);
+        float2 tmp[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) o[m][k] = tmp[k];
+        for (int k = 0; k < 16; ++k) tmp[k] = x[perm16(k)];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = tmp[k];
+      }
     } else if constexpr (kR3 == 8) {
       const float2 u4 = cmul(u2, u2);
-      o[m][4] = cmul(o[m][4], u4);
-      o[m][5] = cmul(o[m][5], cmul(u4, u1));
-      o[m][6] = cmul(o[m][6], cmul(u4, u2));
-      o[m][7] = cmul(o[m][7], cmul(u4, u3));
-      dft8<INV>(o[m]);
-      // natural order: X[k] sits in slot perm8(k)
-      float2 tmp[8];
+      const float2 u5 = cmul(u4, u1), u6 = cmul(u4, u2), u7 = cmul(u4, u3);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) tmp[k] = o[m][perm8(k)];
+      for (int q = 0; q < NT; ++q) {
+        float2 (&x)[kR3] = o[q][m];
+        x[1] = cmul(x[1], u1);   x[2] = cmul(x[2], u2);   x[3] = cmul(x[3], u3);   x[4] = cmul(x[4], u4);
+        x[5] = cmul(x[5], u5);   x[6] = cmul(x[6], u6);   x[7] = cmul(x[7], u7);
+        dft8<INV>(x);
+        // natural order: X[k] sits in slot perm8(k)
+        float2 tmp[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[m][k] = tmp[k];
+        for (int k = 0; k < 8; ++k) tmp[k] = x[perm8(k)];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = tmp[k];
+      }
     } else {
-      dft4<INV>(o[m][0], o[m][1], o[m][2], o[m][3]);
+#pragma unroll
+      for (int q = 0; q < NT; ++q) {
+        float2 (&x)[kR3] = o[q][m];
+        x[1] = cmul(x[1], u1);   x[2] = cmul(x[2], u2);   x[3] = cmul(x[3], u3);
+        dft4<INV>(x[0], x[1], x[2], x[3]);
+      }
     }
   }
+}
+
+template <bool INV>
+__device__ __forceinline__ void fft_core(float2 (&v)[16], FftSmem& s, const float2* __restrict__ tw, int t, int bar,
+                                         float2 (&o)[kM3][kR3]) {
+  fft_core_n<INV, 1>(reinterpret_cast<float2 (&)[1][16]>(v), &s, tw, t, bar,
+                     reinterpret_cast<float2 (&)[1][kM3][kR3]>(o));
 }
 
 // exp(+i*pi*kGroup*r/(2P)) = exp(i*pi*r/32): the r-dependent factor of the twist zeta^(t + kGroup r) (kGroup = P/16),
@@ -279,6 +314,31 @@ __device__ __forceinline__ void fwd_block_to_global(const float (&a)[16], float2
   for (int m = 0; m < kM3; ++m)
 #pragma unroll
     for (int k = 0; k < kR3; ++k) spec[t + kGroup * m + 256 * k] = o[m][k];
+  group_sync(bar);  // pass-C gathers done before the next transform's scatter
+}
+
+// NT blocks at once (fft_core_n): a[q] = real samples of block q, spec[q] = destination or nullptr (block not stored).
+template <int NT>
+__device__ __forceinline__ void fwd_blocks_to_global(const float (&a)[NT][16], float2 zt, FftSmem* __restrict__ s,
+                                                     const float2* __restrict__ tw, int t, int bar,
+                                                     float2* (&spec)[NT]) {
+  float2 v[NT][16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const float2 z = (r == 0) ? zt : cmul(zt, zeta_step(r));
+#pragma unroll
+    for (int q = 0; q < NT; ++q) v[q][r] = make_float2(a[q][r] * z.x, a[q][r] * z.y);
+  }
+  float2 o[NT][kM3][kR3];
+  fft_core_n<false, NT>(v, s, tw, t, bar, o);
+#pragma unroll
+  for (int q = 0; q < NT; ++q)
+    if (spec[q]) {
+#pragma unroll
+      for (int m = 0; m < kM3; ++m)
+#pragma unroll
+        for (int k = 0; k < kR3; ++k) __stcg(spec[q] + t + kGroup * m + 256 * k, o[q][m][k]);
+    }
   group_sync(bar);  // pass-C gathers done before the next transform's scatter
 }
 

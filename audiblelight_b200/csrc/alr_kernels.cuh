@@ -64,6 +64,10 @@ struct EvDev {
   int dry_channel, dry_low, dry_high;
   const float* xnorm;    // optional scalar the dry audio is multiplied with (peak normalisation), or NULL
   double snr, ref_db;
+  // moving events rendered by the persistent producer/consumer launch (alr_fused.cuh); 0 for everything else
+  int fused;             // 1: H spectra live in the L2-resident ring, a_l is applied by the C-tasks
+  int fo0;               // ordinal of the event's first RIR among the chunk's fused RIRs (ready / consumed counters)
+  long long ecap0;       // first entry of the event's (RIR, capsule) tap-energy table
 };
 
 struct IrDev {
@@ -73,6 +77,8 @@ struct IrDev {
   int woff;   // offset of this IR's cross-fade weight band
   int jmin;   // first STFT frame (row of the interpolation matrix) of the band
   int nrows;  // band length
+  int hring;  // fused events: first spectrum slot of this RIR in the ring ([k][c] order), else 0
+  int pad;
 };
 
 struct EvStat {
@@ -133,16 +139,21 @@ __device__ __forceinline__ float warp_max(float v) {
 // k_ir_fft: one group of kGroup threads per RIR partition (event e, IR l, partition k, capsule c), kIrTasks
 // consecutive partitions per group.
 // Spectrum slot = hslot0 + (l*K + k)*C + c, i.e. layout [l][k][c][P] so that k_cmac reads the C capsules of one
-// (l,k) contiguously.  Also writes the partition's energy sum(h^2) for normalize_irs.
+// (l,k) contiguously.  Also writes the partition's energy sum(h^2) for normalize_irs: every WARP stores its own
+// partial (kEnWarps floats per slot, summed in a fixed order by k_ir_scale). Round 1 reduced the warps through a
+// shared-memory buffer that thread 0 read behind the transform's group barrier while the next task's writes were
+// already under way in other warps; a single-buffered version of that mixed the energies of neighbouring tasks
+// about every second run of a 40-event batch (racecheck blind), and the double-buffered fix was never explained.
+// There is no shared reduction state any more: nothing is read that another warp may be rewriting.
 #ifndef ALR_IRFFT_MINB  // occupancy experiment, profiles/r01_irfft_occupancy.txt: 4 CTAs per SM (64 registers) is fastest
 #define ALR_IRFFT_MINB 4
 #endif
+constexpr int kEnWarps = kGroup / 32;  // energy partials per spectrum slot
 __global__ void __launch_bounds__(kCtaThreads, ALR_IRFFT_MINB)
 k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, int n_tasks,
          const float2* __restrict__ tw, const float2* __restrict__ zeta, float2* __restrict__ hspec,
          float* __restrict__ hen) {
   __shared__ FftSmem sm[kGroupsPerCta];
-  __shared__ float s_red[kGroupsPerCta][2][kGroup / 32];
   const int g = threadIdx.x / kGroup, t = threadIdx.x % kGroup, bar = 1 + g;
   // Each group transforms kIrTasks consecutive partitions: the event lookup (a chain of ~8 dependent loads) and the
   // descriptor reads are paid once per group instead of once per transform (consecutive tasks share the event).
@@ -178,21 +189,8 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
     }
     const long long slot = ev.hslot0 + (long long)(l * ev.K + k) * ev.C + c;
     en = warp_sum(en);
-    // The partial sums are double-buffered by task parity: buffer i & 1 is read after this task's transform (>= 4 group
-    // barriers after the writes) and rewritten two tasks later, so the loop needs no barrier of its own (the
-    // transform's trailing barrier protects the exchange buffer). A first version used a single buffer and a named
-    // barrier at the end of the loop body, right behind the thread-0-only block below: about every second run of a
-    // 40-event batch the energies of neighbouring tasks got mixed (per-IR scales off by 15 %; compute-sanitizer's
-    // racecheck saw nothing, the timing changes under the tool). tests/test_gpu_configs.py::
-    // test_many_events_one_call_matches_individual_calls caught it; the mechanism was not pinned down further.
-    if ((t & 31) == 0) s_red[g][i & 1][t >> 5] = en;
+    if ((t & 31) == 0) hen[slot * kEnWarps + (t >> 5)] = en;
     fwd_block_to_global(a, zt, sm[g], tw, t, bar, hspec + slot * kP);  // contains group barriers, ends with one
-    if (t == 0) {
-      float tot = 0.f;
-#pragma unroll
-      for (int w = 0; w < kGroup / 32; ++w) tot += s_red[g][i & 1][w];
-      hen[slot] = tot;
-    }
   }
 }
 
@@ -205,6 +203,7 @@ __global__ void k_ir_scale(const EvDev* __restrict__ evs, int n_ev, const int* _
   const int e = find_segment(ir_prefix, n_ev, w);
   const EvDev& ev = evs[e];
   const int l = w - __ldg(ir_prefix + e);
+  if (ev.fused) return;  // a_l of fused events comes from the P-tasks of k_mov_fused
   double a = 1.0;
   if (ev.gain_mode == kGainDry) {
     a = stats[ev.parent].a0;  // the parent's a_0: compute_dry_audio gets the normalised IRs (synthesize.py:608)
@@ -212,7 +211,13 @@ __global__ void k_ir_scale(const EvDev* __restrict__ evs, int n_ev, const int* _
     double mean_e = 0.0;
     for (int c = 0; c < ev.C; ++c) {
       float s = 0.f;
-      for (int k = lane; k < ev.K; k += 32) s += hen[ev.hslot0 + (long long)(l * ev.K + k) * ev.C + c];
+      for (int k = lane; k < ev.K; k += 32) {
+        const float* p = hen + (ev.hslot0 + (long long)(l * ev.K + k) * ev.C + c) * kEnWarps;
+        float sk = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < kEnWarps; ++w4) sk += p[w4];
+        s += sk;
+      }
       s = warp_sum(s);
       mean_e += sqrt((double)s) + 2.2250738585072014e-308;
     }
@@ -273,7 +278,8 @@ k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix,
     const IrDev ir = irs[ev.ir0 + l];
     const int j = local - ir.xslot;
     const int t0 = (ir.xb0 + j) * kP;
-    const float sc = irscale[ev.ir0 + l] * (ev.xnorm ? __ldg(ev.xnorm) : 1.f);
+    // fused events: the C-tasks of k_mov_fused apply 512 a_l themselves (a_l is not known yet when this kernel runs)
+    const float sc = (ev.fused ? 1.f : irscale[ev.ir0 + l]) * (ev.xnorm ? __ldg(ev.xnorm) : 1.f);
     const float* __restrict__ x = ev.x;
     // sin^2(pi p / 256) for the in-frame positions of this thread's samples: offset t + kGroup r inside the block, i.e.
     // p = t (+ 64 for odd r when kGroup == 64)
@@ -683,8 +689,7 @@ k_cmac_static(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ p
 #endif
 __global__ void __launch_bounds__(kCtaThreads, ALR_IFFT_MINB)
 k_ifft_ola(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const float2* __restrict__ tw,
-           const float2* __restrict__ zeta, const float2* __restrict__ yspec, float2* __restrict__ partials,
-           int part_base) {
+           const float2* __restrict__ zeta, const float2* __restrict__ yspec, float2* __restrict__ partials) {
   __shared__ FftSmem sm[kGroupsPerCta];
   __shared__ float s_max[kCtaThreads / 32], s_sum[kCtaThreads / 32];
   const int g = threadIdx.x / kGroup, t = threadIdx.x % kGroup, bar = 1 + g;
@@ -753,7 +758,6 @@ k_ifft_ola(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ pref
     // slot relative to the EVENT's range: events without IRs (k_tile) own partial slots too, so the chunk-wide CTA
     // index is not the slot index (found by tests/test_gpu_fuzz.py: every event after a no-IR event got a wrong gain)
     partials[ev.part0 + local] = make_float2(m, s);
-    (void)part_base;
   }
 }
 

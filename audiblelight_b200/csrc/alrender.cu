@@ -18,6 +18,7 @@
 
 #include "../../include/alrender.h"
 #include "alr_kernels.cuh"
+#include "alr_fused.cuh"
 
 using namespace alr;
 
@@ -89,7 +90,7 @@ struct HostBuf {  // pinned
   }
 };
 
-enum ProfCat { kCatIrFft = 0, kCatXFft, kCatCmac, kCatCmacStatic, kCatIfft, kCatMix, kCatOther, kNumCat };
+enum ProfCat { kCatIrFft = 0, kCatXFft, kCatCmac, kCatCmacStatic, kCatIfft, kCatMix, kCatOther, kCatFused, kNumCat };
 
 }  // namespace
 
@@ -98,7 +99,13 @@ struct alr_context {
   float2* d_tw = nullptr;    // exp(-2 pi i m / P), m < P
   float2* d_zeta = nullptr;  // exp(+i pi t / 2P), t < 64 (twist seed of thread t)
   float* d_win = nullptr;  // sin^2(pi p / 256), p < 128
-  DevBuf spec, desc, misc, arena, augbuf, augdesc;
+  DevBuf spec, desc, misc, arena, augbuf, augdesc, ring;
+  // persistent producer/consumer launch for moving events (alr_fused.cuh)
+  int fused = 0;                          // ALR_FUSED=1: moving events through k_mov_fused (experiment, see profiles/r02_fused_ring.txt)
+  int64_t ring_bytes = (int64_t)64 << 20; // H-spectra ring (must stay L2 resident: 126 MB on B200)
+  int lookahead = 2;                      // runs whose RIRs are produced ahead of the consumer tasks
+  int fused_grid = 0;                     // resident CTAs of k_mov_fused (SMs x occupancy)
+  int sm_clock_khz = 0;
   HostBuf stage, stage_out, stage_aug;
   int64_t ws_limit = (int64_t)4 << 30;  // 4 GiB: 3 % faster than 2 GiB on the benchmark (fewer, fuller launches); 8 GiB adds 1 %
   int profiling = 0;
@@ -146,9 +153,13 @@ struct EvSize {
   int n_blk = 0;                   // lrange entries
   int n_irfft = 0, n_cmac = 0, n_cmac_static = 0, n_ifft = 0, n_parts = 0;
   bool pass = false;
+  // moving events taken by k_mov_fused: H lives in the ring (z.h_ws = 0), tasks instead of k_ir_fft / k_cmac CTAs
+  bool fused = false;
+  long long h_ws = 0;  // H slots in the chunk workspace
+  int n_ptask = 0, n_ctask = 0;
 };
 
-int size_event(const alr_event& u, int idx, EvSize& z) {
+int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0) {
   z = EvSize();
   if (u.n_channels < 1) return fail(ALR_ERR_INVALID, "event %d: n_channels must be >= 1", idx);
   if (u.n_out < 1 || !u.spatial) return fail(ALR_ERR_INVALID, "event %d: no output buffer", idx);
@@ -197,14 +208,52 @@ int size_event(const alr_event& u, int idx, EvSize& z) {
     if (wb > 0x3fffffff) return fail(ALR_ERR_INVALID, "event %d: too many STFT frames", idx);
     z.xb = xb;
     z.wband = (int)wb;
+    // Eligibility for the fused launch: the RIRs any single run of kGm output blocks reads (its dependency window)
+    // plus the one being produced must fit the ring. Upper bound from the un-tightened bands (same expressions as
+    // above); the planner's own ordering adapts to anything smaller than that.
+    if (ring_slots > 0 && C <= 0x7fff && z.B_valid > 0) {
+      static thread_local std::vector<int> fb, le;  // first / last active source block per RIR (-1: inactive)
+      fb.assign(N, -1);
+      le.assign(N, -1);
+      for (int l = 0; l < N; ++l) {
+        const int lo = (l > 0 ? fr[l - 1] : fr[0]) - 1, hi = (l < N - 1 ? fr[l + 1] : fr[N - 1]) - 1;
+        const long long t_lo = std::max<long long>(0, 128LL * lo - 128), t_hi = std::min<long long>(z.xlimit, 128LL * hi + 128);
+        if (t_hi > t_lo) {
+          fb[l] = (int)(t_lo / kP);
+          le[l] = (int)((t_hi - 1) / kP);
+        }
+      }
+      int wmax = 0, lmin = 0;
+      for (int b0 = 0; b0 < z.B_valid; b0 += kGm) {
+        const int b1 = std::min(b0 + kGm, z.B_valid) - 1;
+        while (lmin < N && (fb[lmin] < 0 || le[lmin] + z.K - 1 < b0)) ++lmin;
+        int lmax = lmin - 1;
+        for (int l = lmin; l < N && (fb[l] < 0 || fb[l] <= b1); ++l)
+          if (fb[l] >= 0) lmax = l;
+        wmax = std::max(wmax, lmax - lmin + 1);
+      }
+      const long long ir_slots = (long long)z.K * C;
+      z.fused = (long long)(wmax + 2) * ir_slots <= ring_slots;
+    }
   }
   const int ncg = (C + kChanGroup - 1) / kChanGroup;
   const long long n_cmac = (long long)ceil_div(z.B_valid, kGm) * ncg * kBinCtas;
   const long long n_ifft = (long long)((C + kIfftCh - 1) / kIfftCh) * ceil_div(z.B_out, kRun);
   if (z.h > 0x3ffffff0LL || n_cmac > 0x3ffffff0LL || z.xb > 0x3ffffff0LL)
     return fail(ALR_ERR_INVALID, "event %d: too large for 32-bit task indices", idx);
+  z.h_ws = z.h;
   z.n_irfft = (int)z.h;
   z.n_cmac = moving ? (int)n_cmac : 0;         // generic kernel: moving events
+  if (z.fused) {
+    if ((long long)N * C > 0x3ffffff0LL) z.fused = false;
+  }
+  if (z.fused) {
+    z.n_ptask = N * C;
+    z.n_ctask = (int)n_cmac;
+    z.h_ws = 0;
+    z.n_irfft = 0;
+    z.n_cmac = 0;
+  }
   const long long n_cmac_s = (long long)ceil_div(z.B_valid, kG) * ((C + kStaticCh - 1) / kStaticCh) * kBinCtas;
   z.n_cmac_static = moving ? 0 : (int)n_cmac_s;  // regular block-FIR kernel: static events
   z.n_ifft = (int)n_ifft;
@@ -328,6 +377,10 @@ struct Chunk {
   size_t bytes = 0;  // blob size
   size_t base = 0;   // offset of the blob in the staging / descriptor buffers
   int part_base = 0, ir_base = 0, gain_base = 0;
+  // fused launch: RIRs, tasks and (RIR, capsule) energy entries of the chunk's fused events
+  int n_fo = 0, n_tasks = 0;
+  long long n_ecap = 0;
+  size_t off_tasks = 0, off_pop = 0, off_ncons = 0;
 };
 
 void layout_chunk(Chunk& ch) {
@@ -350,6 +403,9 @@ void layout_chunk(Chunk& ch) {
   ch.off_ifft = take((size_t)(ne + 1) * sizeof(int));
   ch.off_tile = take((size_t)ne * sizeof(int));
   ch.off_dry = take((size_t)ne * sizeof(int));
+  ch.off_tasks = take((size_t)ch.n_tasks * sizeof(FusedTask));
+  ch.off_pop = take((size_t)ch.n_fo * sizeof(int2));
+  ch.off_ncons = take((size_t)ch.n_fo * sizeof(int2));
   ch.bytes = align_up(o, 256);
 }
 
@@ -364,10 +420,16 @@ void make_chunks(const std::vector<EvSize>& sz, int64_t ws_limit, std::vector<Ch
     long long bytes = 0;
     while (e < n) {
       const EvSize& z = sz[e];
-      const long long add = (z.h + z.xb + z.y) * slot_bytes;
+      const long long add = (z.h_ws + z.xb + z.y) * slot_bytes;
       if (e > ch.ev_begin && bytes + add > ws_limit) break;
+      if (e > ch.ev_begin && z.fused && (long long)ch.n_tasks + z.n_ptask + z.n_ctask > 0x3ffffff0LL) break;
       bytes += add;
-      ch.hslots += z.h;
+      ch.hslots += z.h_ws;
+      if (z.fused) {
+        ch.n_fo += z.n_ir;
+        ch.n_tasks += z.n_ptask + z.n_ctask;
+        ch.n_ecap += (long long)z.n_ptask;
+      }
       ch.xslots += z.xb;
       ch.yslots += z.y;
       ch.n_ir += z.n_ir;
@@ -379,6 +441,112 @@ void make_chunks(const std::vector<EvSize>& sz, int64_t ws_limit, std::vector<Ch
     layout_chunk(ch);
     out.push_back(ch);
   }
+}
+
+// ---- task queue of the fused launch ---------------------------------------------------------------------------------
+// Orders the P- and C-tasks of a chunk's fused events (see alr_fused.cuh) and assigns ring regions.
+//   * events are processed one after the other, runs in ascending order; before the C-tasks of run i are queued, the
+//     P-tasks of every RIR that run i + lookahead reads are queued (across event boundaries), so consumers find their
+//     inputs ready and the queue never makes a CTA wait for a task that comes later;
+//   * a RIR gets the next K*C slots of the ring (wrapping to 0 when it does not fit behind the head); the RIRs whose
+//     region it overwrites are recorded in pop[] — its P-tasks wait until consumed[] shows all their readers done. If
+//     one of those readers has not even been queued yet (ring tighter than lookahead), its run is queued first, i.e.
+//     the lookahead shrinks on the spot. size_event() admitted the event only if a single run's window fits the ring,
+//     so that always works.
+// Returns false on an internal inconsistency (never expected).
+struct FusedRun {
+  int ev, run, lmin, lmax;  // lmax < lmin: the run reads no RIR
+};
+bool plan_fused(EvDev* evs, int ne, IrDev* irs, const int2* lr, long long ring_slots, int lookahead,
+                FusedTask* tasks, int n_tasks_expected, int2* pop, int2* need, int n_fo_expected) {
+  static thread_local std::vector<FusedRun> runs;
+  static thread_local std::vector<int> last_run;      // per fused RIR ordinal: global index of the last run reading it
+  static thread_local std::vector<int> fo_ev;         // per fused ordinal: event
+  runs.clear();
+  int n_fo = 0;
+  for (int e = 0; e < ne; ++e) {
+    EvDev& d = evs[e];
+    if (!d.fused) continue;
+    d.fo0 = n_fo;
+    n_fo += d.N;
+    const int nruns = ceil_div(d.B_valid, kGm);
+    for (int r = 0; r < nruns; ++r) {
+      const int b0 = r * kGm, nb = std::min(kGm, d.B_valid - b0);
+      runs.push_back({e, r, lr[d.blk0 + b0].x, lr[d.blk0 + b0 + nb - 1].y});
+    }
+  }
+  if (n_fo != n_fo_expected) return false;
+  last_run.assign(n_fo, -1);
+  fo_ev.resize(n_fo);
+  for (int i = 0; i < n_fo; ++i) need[i] = make_int2(0, 0);
+  for (int e = 0; e < ne; ++e)
+    if (evs[e].fused)
+      for (int l = 0; l < evs[e].N; ++l) {
+        fo_ev[evs[e].fo0 + l] = e;
+        need[evs[e].fo0 + l].y = evs[e].C + 1;  // ready[] value of a published RIR
+      }
+  for (int i = 0; i < (int)runs.size(); ++i) {
+    const FusedRun& r = runs[i];
+    const EvDev& d = evs[r.ev];
+    const int per_run = ((d.C + kChanGroup - 1) / kChanGroup) * kBinCtas;
+    for (int l = r.lmin; l <= r.lmax; ++l) {
+      need[d.fo0 + l].x += per_run;
+      last_run[d.fo0 + l] = i;
+    }
+  }
+  int nt = 0;
+  int c_emitted = 0;          // runs [0, c_emitted) have their C-tasks queued
+  int p_emitted = 0;          // fused ordinals [0, p_emitted) have their P-tasks queued
+  long long head = 0;         // next free ring slot
+  int live_lo = 0;            // ordinals [live_lo, p_emitted) occupy ring regions
+  static thread_local std::vector<long long> reg_lo;  // ring region start per ordinal
+  reg_lo.resize(n_fo);
+  bool ok = true;
+  auto emit_c = [&](int i) {
+    const FusedRun& r = runs[i];
+    const EvDev& d = evs[r.ev];
+    const int per_run = ((d.C + kChanGroup - 1) / kChanGroup) * kBinCtas;
+    for (int s = 0; s < per_run; ++s) tasks[nt++] = FusedTask{kTaskC, r.ev, r.run, s};
+  };
+  auto emit_p = [&](int fo) {  // queue the P-tasks of ordinal fo (== p_emitted)
+    const int e = fo_ev[fo];
+    const EvDev& d = evs[e];
+    const int l = fo - d.fo0;
+    const long long size = (long long)d.K * d.C;
+    if (head + size > ring_slots) head = 0;
+    const long long lo = head, hi = head + size;
+    // previous occupants overlapping [lo, hi): a prefix of the live list (the ring is a FIFO)
+    int pop_lo = live_lo;
+    while (live_lo < fo) {
+      const EvDev& o = evs[fo_ev[live_lo]];
+      const long long olo = reg_lo[live_lo], ohi = olo + (long long)o.K * o.C;
+      if (ohi <= lo || olo >= hi) break;
+      // its readers must be in the queue before this producer
+      while (c_emitted <= last_run[live_lo]) {
+        if (runs[c_emitted].lmax >= 0 && evs[runs[c_emitted].ev].fo0 + runs[c_emitted].lmax >= fo) ok = false;
+        emit_c(c_emitted++);
+      }
+      ++live_lo;
+    }
+    reg_lo[fo] = lo;
+    head = hi;
+    irs[d.ir0 + l].hring = (int)lo;
+    pop[fo] = make_int2(pop_lo, live_lo);
+    for (int c = 0; c < d.C; ++c) tasks[nt++] = FusedTask{kTaskP, e, l, c};
+    p_emitted = fo + 1;
+  };
+  for (int i = 0; i < (int)runs.size(); ++i) {
+    if (i < c_emitted) continue;  // pulled forward by a tight ring
+    const FusedRun& tgt = runs[std::min<int>(i + lookahead, (int)runs.size() - 1)];
+    // everything of earlier events, and RIRs <= lmax of the target run
+    int upto = evs[tgt.ev].fo0 + (tgt.lmax >= tgt.lmin ? tgt.lmax + 1 : 0);
+    // the run itself must have its inputs whatever the lookahead target says
+    if (runs[i].lmax >= runs[i].lmin) upto = std::max(upto, evs[runs[i].ev].fo0 + runs[i].lmax + 1);
+    while (p_emitted < upto && i >= c_emitted) emit_p(p_emitted);
+    if (i >= c_emitted) emit_c(c_emitted++);
+  }
+  while (p_emitted < n_fo) emit_p(p_emitted);  // RIRs no run reads (their a_0 may still be needed by a dry render)
+  return ok && nt == n_tasks_expected;
 }
 
 // ---- profiling helpers ---------------------------------------------------------------------------------------
@@ -486,6 +654,26 @@ int alr_create(int device, alr_context** out) {
     delete ctx;
     return rc;
   }
+  {
+    // k_mov_fused is a persistent launch: exactly as many CTAs as can be resident at once
+    int sms = 0, per_sm = 0, khz = 0;
+    cudaError_t e1 = cudaFuncSetAttribute(k_mov_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
+    cudaError_t e2 = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaError_t e3 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mov_fused, kCtaThreads, kFusedSmem);
+    cudaError_t e4 = cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || sms < 1 || per_sm < 1) {
+      cudaGetLastError();
+      ctx->fused = 0;  // unfused kernels only
+      ctx->fused_grid = 0;
+    } else {
+      ctx->fused_grid = sms * per_sm;
+      ctx->sm_clock_khz = std::max(khz, 500000);
+    }
+    const bool fused_ok = ctx->fused_grid > 0;
+    if (const char* v = getenv("ALR_FUSED")) ctx->fused = fused_ok && atoi(v) != 0;
+    if (const char* v = getenv("ALR_RING_MB")) ctx->ring_bytes = std::max<int64_t>(1, atoll(v)) << 20;
+    if (const char* v = getenv("ALR_LOOKAHEAD")) ctx->lookahead = std::max(0, atoi(v));
+  }
   *out = ctx;
   return ALR_OK;
 }
@@ -503,6 +691,7 @@ void alr_destroy(alr_context* ctx) {
   ctx->arena.release();
   ctx->augbuf.release();
   ctx->augdesc.release();
+  ctx->ring.release();
   ctx->stage.release();
   ctx->stage_out.release();
   ctx->stage_aug.release();
@@ -822,6 +1011,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     dry_events.push_back(sdry);
     dry_parent.push_back((int)i);
   }
+  const long long ring_slots = ctx->fused ? (long long)(ctx->ring_bytes / ((int64_t)kP * sizeof(float2))) : 0;
   const std::vector<alr_event>* phase_events[2] = {&events, &dry_events};
   std::vector<EvSize> sizes[2];
   std::vector<Chunk> chunks[2];
@@ -829,13 +1019,14 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     const auto& evl = *phase_events[ph];
     sizes[ph].resize(evl.size());
     for (size_t i = 0; i < evl.size(); ++i) {
-      int rc = size_event(evl[i], ph == 0 ? (int)i : dry_parent[i], sizes[ph][i]);
+      int rc = size_event(evl[i], ph == 0 ? (int)i : dry_parent[i], sizes[ph][i], ph == 0 ? ring_slots : 0);
       if (rc) return rc;
     }
     // host mode: smaller chunks give the upload / compute / download pipeline something to overlap
     make_chunks(sizes[ph], host_mode ? std::min<int64_t>(ctx->ws_limit, (int64_t)512 << 20) : ctx->ws_limit, chunks[ph]);
   }
-  long long max_h = 0, max_x = 0, max_y = 0;
+  long long max_h = 0, max_x = 0, max_y = 0, max_ecap = 0;
+  int max_fo = 0;
   size_t blob_total = 0;
   int part_total = 0, ir_total = 0, gain_total = 0;
   for (int ph = 0; ph < 2; ++ph)
@@ -843,6 +1034,8 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       max_h = std::max(max_h, ch.hslots);
       max_x = std::max(max_x, ch.xslots);
       max_y = std::max(max_y, ch.yslots);
+      max_fo = std::max(max_fo, ch.n_fo);
+      max_ecap = std::max(max_ecap, ch.n_ecap);
       ch.base = blob_total;
       blob_total += ch.bytes;
       ch.part_base = part_total;
@@ -951,7 +1144,10 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     return o;
   };
   const size_t mo_irscale = m_take(std::max<size_t>(ir_total, 1) * sizeof(float));
-  const size_t mo_hen = m_take(std::max<size_t>((size_t)max_h, 1) * sizeof(float));
+  const size_t mo_hen = m_take(std::max<size_t>((size_t)max_h, 1) * kEnWarps * sizeof(float));
+  const size_t mo_ctl = m_take(sizeof(FusedCtl));
+  const size_t mo_flags = m_take(std::max<size_t>((size_t)max_fo, 1) * 2 * sizeof(int));  // ready[], consumed[]
+  const size_t mo_ecap = m_take(std::max<size_t>((size_t)max_ecap, 1) * sizeof(float));
   const size_t mo_parts = m_take(std::max<size_t>(part_total, 1) * sizeof(float2));
   const size_t mo_gain = m_take(std::max<size_t>(gain_total, 1) * sizeof(float));
   const size_t mo_stats = m_take(std::max<size_t>(n_events, 1) * sizeof(EvStat));
@@ -959,8 +1155,12 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
   {
     int rc = ctx->misc.ensure(m_off);
     if (rc) return rc;
-    rc = ctx->stage_out.ensure(std::max<size_t>(n_events, 1) * sizeof(EvStat));
+    rc = ctx->stage_out.ensure(std::max<size_t>(n_events, 1) * sizeof(EvStat) + sizeof(FusedCtl));
     if (rc) return rc;
+    if (max_fo > 0) {
+      rc = ctx->ring.ensure((size_t)ctx->ring_bytes);
+      if (rc) return rc;
+    }
   }
   char* mbase = (char*)ctx->misc.p;
   float* d_irscale = (float*)(mbase + mo_irscale);
@@ -971,7 +1171,11 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     if (mev_event[k] >= 0) h_mevs[k].gain = d_gain + mev_event[k];
   EvStat* d_stats = (EvStat*)(mbase + mo_stats);
   float* d_ambparts = (float*)(mbase + mo_amb);
+  FusedCtl* d_ctl = (FusedCtl*)(mbase + mo_ctl);
+  int* d_flags = (int*)(mbase + mo_flags);
+  float* d_ecap = (float*)(mbase + mo_ecap);
   CUDA_TRY(cudaMemsetAsync(d_stats, 0, std::max<size_t>(n_events, 1) * sizeof(EvStat), st));
+  CUDA_TRY(cudaMemsetAsync(d_ctl, 0, sizeof(FusedCtl), st));
   ctx->prof.workspace_bytes = (int64_t)(ctx->spec.cap + ctx->misc.cap + ctx->desc.cap + ctx->arena.cap);
   ctx->prof.n_chunks = (int64_t)(chunks[0].size() + chunks[1].size());
   {
@@ -1245,7 +1449,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       int* l_tile = (int*)(hb + ch.off_tile);
       int* l_dry = (int*)(hb + ch.off_dry);
       int n_tile = 0, n_dry = 0, ir_off = 0, w_off = 0, blk_off = 0, parts = ch.part_base;
-      long long hs = 0, xs = 0, ys = 0;
+      long long hs = 0, xs = 0, ys = 0, ecap_off = 0;
       p_irfft[0] = p_ir[0] = p_xfft[0] = p_cmac[0] = p_cmacs[0] = p_ifft[0] = 0;
       for (int i = 0; i < ne; ++i) {
         const int ei = ch.ev_begin + i;
@@ -1270,7 +1474,12 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         d.yslot0 = ys;
         d.part0 = parts;
         d.nparts = z.n_parts;
-        hs += z.h;
+        if (z.fused) {
+          d.fused = 1;
+          d.ecap0 = ecap_off;
+          ecap_off += z.n_ptask;
+        }
+        hs += z.h_ws;
         xs += z.xb;  // the bound, so that slot bases do not depend on the detailed plan
         ys += z.y;
         parts += z.n_parts;
@@ -1285,6 +1494,10 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         p_ifft[i + 1] = p_ifft[i] + z.n_ifft;
         if (!z.pass && d.N == 0) l_tile[n_tile++] = i;
       }
+      if (ch.n_tasks > 0 &&
+          !plan_fused(h_evs, ne, h_irs, h_lr, ring_slots, ctx->lookahead, (FusedTask*)(hb + ch.off_tasks), ch.n_tasks,
+                      (int2*)(hb + ch.off_pop), (int2*)(hb + ch.off_ncons), ch.n_fo))
+        return fail(ALR_ERR_INVALID, "internal: inconsistent task plan for the fused launch");
       host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
       // Descriptors. In host mode they travel on the UPLOAD stream, right behind this chunk's inputs and ahead of the
       // next chunk's: a copy on the compute stream would sit behind everything already queued on the H2D copy
@@ -1331,6 +1544,32 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
                                                                        ctx->d_win, d_xspec);
         LAUNCH_CHECK(kCatXFft);
       }
+      if (ch.n_tasks > 0) {
+        CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)ch.n_fo * 2 * sizeof(int), st));
+        CUDA_TRY(cudaMemsetAsync(&d_ctl->ticket, 0, sizeof(int), st));
+        FusedArgs fa;
+        fa.evs = c_evs;
+        fa.irs = c_irs;
+        fa.lrange = c_lr;
+        fa.tasks = (const FusedTask*)(db + ch.off_tasks);
+        fa.n_tasks = ch.n_tasks;
+        fa.pop = (const int2*)(db + ch.off_pop);
+        fa.need = (const int2*)(db + ch.off_ncons);
+        fa.ctl = d_ctl;
+        fa.ready = d_flags;
+        fa.consumed = d_flags + ch.n_fo;
+        fa.ecap = d_ecap;
+        fa.irscale = c_irscale;
+        fa.stats = d_stats;
+        fa.tw = ctx->d_tw;
+        fa.zeta = ctx->d_zeta;
+        fa.xspec = d_xspec;
+        fa.hring = (float2*)ctx->ring.p;
+        fa.yspec = d_yspec;
+        fa.spin_limit = (long long)ctx->sm_clock_khz * 2000LL;  // ~2 s of SM clocks
+        k_mov_fused<<<std::min(ctx->fused_grid, ch.n_tasks), kCtaThreads, kFusedSmem, st>>>(fa);
+        LAUNCH_CHECK(kCatFused);
+      }
       if (n_cmac > 0) {
         k_cmac<<<n_cmac, kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_cmac), c_irs, c_lr, d_xspec, d_hspec,
                                               d_yspec);
@@ -1343,7 +1582,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       }
       if (n_ifft > 0) {
         k_ifft_ola<<<n_ifft, kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_ifft), ctx->d_tw, ctx->d_zeta,
-                                                  d_yspec, d_parts, ch.part_base);
+                                                  d_yspec, d_parts);
         LAUNCH_CHECK(kCatIfft);
       }
       if (n_tile > 0) {
@@ -1401,9 +1640,12 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
   ctx->prof.ms_host_plan = host_plan_ms;
 
   // ---- results back ---------------------------------------------------------------------------------------------------
+  FusedCtl* h_ctl = (FusedCtl*)((char*)ctx->stage_out.p + std::max<size_t>(n_events, 1) * sizeof(EvStat));
+  h_ctl->abort = 0;
   if (n_events > 0) {
     CUDA_TRY(cudaMemcpyAsync(ctx->stage_out.p, d_stats, n_events * sizeof(EvStat), cudaMemcpyDeviceToHost, st));
     ctx->prof.d2h_bytes += (int64_t)(n_events * sizeof(EvStat));
+    if (max_fo > 0) CUDA_TRY(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(FusedCtl), cudaMemcpyDeviceToHost, st));
   }
   if (host_mode) {
     cudaEvent_t ev;  // the caller's stream finishes only when every download has finished
@@ -1423,6 +1665,9 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       cudaEventDestroy(m.ev);
     }
   }
+  if (h_ctl->abort)
+    return fail(ALR_ERR_CUDA, "internal: the producer/consumer launch timed out waiting for a dependency (watchdog); "
+                              "results of this call are invalid");
   float ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
   ctx->prof.ms_total = ms;
@@ -1441,6 +1686,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     ctx->prof.ms_ifft = acc[kCatIfft];
     ctx->prof.ms_mix = acc[kCatMix];
     ctx->prof.ms_other = acc[kCatOther];
+    ctx->prof.ms_fused = acc[kCatFused];
   }
   if (stats_out) {
     const EvStat* hs = (const EvStat*)ctx->stage_out.p;

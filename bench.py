@@ -315,7 +315,7 @@ def main():
     # ---- roofline of the dominant kernel (CUDA events recorded on the render stream between the launches) -------------
     peak, peak_src = load_peaks()
     kern_ms = {k[3:]: prof_acc[k] / args.steps for k in ("ms_ir_fft", "ms_x_fft", "ms_cmac", "ms_cmac_static", "ms_ifft",
-                                                         "ms_mix", "ms_other")}
+                                                         "ms_mix", "ms_other", "ms_fused")}
     dom = max(kern_ms, key=kern_ms.get)
     # algorithmic bytes each kernel class is responsible for (DESIGN.md "Algorithmic bytes"):
     out_bytes = sum(4 * sp.channels * e.n_audio for sp in specs for e in sp.events)
@@ -323,8 +323,8 @@ def main():
     x_bytes = sum(4 * e.n_audio for sp in specs for e in sp.events)
     b_ir_static = sum(4 * sp.channels * e.n_irs * sp.n_ir_samples for sp in specs for e in sp.events if e.n_irs == 1)
     alg = {"ir_fft": b_ir, "x_fft": x_bytes, "cmac": b_ir - b_ir_static, "cmac_static": b_ir_static, "ifft": out_bytes,
-           "mix": out_bytes + mix_bytes, "other": 0}
-    n_launch_dom = {"ir_fft": 1, "x_fft": 1, "cmac": 1, "cmac_static": 1, "ifft": 1}.get(dom, None)
+           "mix": out_bytes + mix_bytes, "other": 0, "fused": b_ir - b_ir_static}
+    n_launch_dom = {"ir_fft": 1, "x_fft": 1, "cmac": 1, "cmac_static": 1, "ifft": 1, "fused": 1}.get(dom, None)
     chunks = max(1, int(prof_acc["n_chunks"] / args.steps))
     launches_dom = chunks if n_launch_dom else None
     dom_ms = kern_ms[dom]
@@ -332,7 +332,7 @@ def main():
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        name = {"ir_fft": "k_ir_fft", "cmac": "k_cmac"}.get(dom)
+        name = {"ir_fft": "k_ir_fft", "cmac": "k_cmac", "fused": "k_mov_fused"}.get(dom)
         if name in tr and args.workload == "c5" and args.scenes_per_gpu == 128:
             traffic = tr[name]["dram_read_bytes"] + tr[name]["dram_write_bytes"]
     except Exception:
@@ -340,7 +340,7 @@ def main():
     per_launch = (lambda v: v / launches_dom) if launches_dom else (lambda v: v)
     roofline = {
         "bound": "hbm", "kernel": {"ir_fft": "k_ir_fft", "x_fft": "k_x_fft", "cmac": "k_cmac", "cmac_static": "k_cmac_static",
-                                   "ifft": "k_ifft_ola",
+                                   "ifft": "k_ifft_ola", "fused": "k_mov_fused",
                                    "mix": "k_mix+k_apply_gain+k_amb_*", "other": "misc"}[dom],
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "traffic_note": "DRAM bytes of one launch under ncu (profiles/ncu_traffic.json); compare with algorithmic_bytes_per_launch",

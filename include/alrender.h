@@ -169,6 +169,7 @@ typedef struct alr_profile {
   double ms_ifft;           /* inverse FFT + overlap-add + reductions kernel */
   double ms_mix;            /* gain + mixdown kernels (incl. ambience reduction) */
   double ms_other;
+  double ms_fused;          /* persistent producer/consumer launch for moving events (k_mov_fused: RIR spectra + multiply-accumulate) */
   double ms_host_plan;       /* host time spent planning (overlaps GPU execution from the second chunk on) */
   int64_t kernel_launches;  /* kernels launched by the call */
   int64_t h2d_bytes;
@@ -208,9 +209,11 @@ int alr_render(alr_context* ctx, const alr_event* events, int64_t n_events, cons
 int alr_get_profile(alr_context* ctx, alr_profile* out);
 
 /* ---- unit-test hooks for the FFT core (device pointers) -------------------------------------------------
- * Forward: n_blocks real blocks of `n_valid` (<= partition) samples each, zero-padded to 2*partition ->
- * packed half spectra (partition complex values per block; bin 0 holds (Re X[0], Re X[partition])).
- * Inverse: packed spectra -> 2*partition real samples per block, scaled by 1/(2*partition). */
+ * Forward: n_blocks real blocks of `n_valid` (<= partition) samples each, implicitly zero-padded to 2*partition,
+ * through the negacyclic fold + twist transform of the kernels (csrc/alr_fft.cuh): `partition` ordinary complex
+ * values per block, (re, im) interleaved; bin k is the block's polynomial evaluated at exp(i*pi*(4k+1)/(2*partition)).
+ * Inverse: such spectra -> 2*partition real samples per block (first half, then the overlap tail), scaled by
+ * 1/partition, so that irfft(rfft(a) * rfft(b)) is the linear convolution of two zero-padded blocks. */
 int alr_partition_size(void);
 
 /* Page-locked host memory for the buffers of ALR_MEM_HOST calls (cudaHostAlloc / cudaFreeHost). Optional: any host
