@@ -365,18 +365,76 @@ def _mix_jobs_for_mic(scene, mic_alias: str, scene_index: int, prerendered: bool
     return sjob, placements
 
 
+class _Thunk:
+    __slots__ = ("fn",)
+
+    def __init__(self, fn):
+        self.fn = fn
+
+
+class LazyPaddedDict(OrderedDict):
+    """`event._spatial_audio_padded` / `_spatial_audio_dry_padded` whose arrays are built on first access.
+
+    The reference materialises a zero-padded (C, T) float32 copy of every event for every microphone inside
+    generate_scene_audio_from_events (synthesize.py:381-395) — 23 MB per event of a one-minute 4-channel scene, most
+    of the 0.49 s that function takes — although only scripts/ssseg/generate_dataset.py ever
+    reads them. Here the dict stores what is needed to build the copy (a reference to the rendered event audio, which
+    render calls replace rather than mutate, and the scene slice) and builds it when somebody asks: same keys, same
+    values, same dtype."""
+
+    def set_lazy(self, key, fn) -> None:
+        OrderedDict.__setitem__(self, key, _Thunk(fn))
+
+    def __getitem__(self, key):
+        v = OrderedDict.__getitem__(self, key)
+        if isinstance(v, _Thunk):
+            v = v.fn()
+            OrderedDict.__setitem__(self, key, v)
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def materialize(self) -> "OrderedDict":
+        return OrderedDict(self.items())
+
+    def __reduce__(self):  # pickling / deepcopy see plain arrays
+        return (OrderedDict, (self.items(),))
+
+
+def _lazy_dict(event, name: str) -> LazyPaddedDict:
+    d = getattr(event, name, None)
+    if not isinstance(d, LazyPaddedDict):
+        d = LazyPaddedDict(d or ())
+        setattr(event, name, d)
+    return d
+
+
 def _store_padded(event, mic_alias, spatial, s0, s1, channels, total, dry) -> None:
-    """Per-event zero-padded copies (synthesize.py:381-395)."""
+    """Per-event zero-padded copies (synthesize.py:381-395), built lazily (LazyPaddedDict)."""
     n = s1 - s0
-    padded = np.zeros((channels, total), dtype=np.float32)
-    take = min(n, spatial.shape[1])
-    padded[:, s0:s0 + take] += spatial[:, :take]
-    event._spatial_audio_padded[mic_alias] = padded
+
+    def build_spatial():
+        padded = np.zeros((channels, total), dtype=np.float32)
+        take = min(n, spatial.shape[1])
+        padded[:, s0:s0 + take] += spatial[:, :take]
+        return padded
+
+    _lazy_dict(event, "_spatial_audio_padded").set_lazy(mic_alias, build_spatial)
     if dry is not None:
-        dpad = np.zeros(total, dtype=np.float32)
-        take = min(n, dry.shape[0])
-        dpad[s0:s0 + take] += dry[:take]
-        event._spatial_audio_dry_padded[mic_alias] = dpad
+        def build_dry():
+            dpad = np.zeros(total, dtype=np.float32)
+            take = min(n, dry.shape[0])
+            dpad[s0:s0 + take] += dry[:take]
+            return dpad
+
+        _lazy_dict(event, "_spatial_audio_dry_padded").set_lazy(mic_alias, build_dry)
 
 
 def generate_scene_audio_from_events(scene) -> None:

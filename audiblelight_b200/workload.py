@@ -176,3 +176,67 @@ def scene_jobs(spec: SceneSpec, arrays, amb, scene_index: int):
     sj = SceneJob(n_channels=spec.channels, n_samples=T, ambience=[amb] if amb is not None else [],
                   ambience_ref_db=[spec.ref_db] if amb is not None else [])
     return jobs, sj
+
+
+# ---- duck-typed Scene / Event / Ambience objects of the same workload ---------------------------------------------------
+# Minimal stand-ins with the attributes the drop-in reads from the reference's classes (core.py / event.py /
+# ambience.py); RIRs are float64 (C, N, Lh) arrays in ordinary (pageable) memory, as the reference's backends deliver
+# them. Used by bench.py (`e2e.objects_mode`) and tools/dataset_throughput.py.
+class SynEmitter:
+    def __init__(self, polar):
+        self.coordinates_relative_polar = polar
+
+
+class SynEvent:
+    def __init__(self, alias, audio, sr, n_irs, snr, start, rng):
+        from collections import OrderedDict
+        self.alias, self.audio, self.sample_rate, self.snr = alias, audio, float(sr), snr
+        self.duration = len(audio) / float(sr)
+        self.scene_start = round(start, 1)  # the DCASE metadata grid is 100 ms
+        self.scene_end = self.scene_start + round(self.duration, 1)
+        self.is_moving = n_irs > 1
+        self.n = n_irs
+        self.class_id, self.filename = int(rng.integers(0, 13)), f"{alias}.wav"
+        self.emitters = [SynEmitter({"mic000": np.array([[rng.uniform(-180, 180), rng.uniform(-40, 40), rng.uniform(0.5, 5)]])})
+                         for _ in range(n_irs)]
+        self.spatial_audio, self._spatial_audio_padded = OrderedDict(), OrderedDict()
+        self._spatial_audio_dry, self._spatial_audio_dry_padded = OrderedDict(), OrderedDict()
+
+    def load_audio(self, ignore_cache=False, normalize=True):
+        return self.audio
+
+    def __len__(self):
+        return self.n
+
+
+class SynAmbience:
+    def __init__(self, noise, ref_db):
+        self.noise, self.ref_db = noise, ref_db
+
+    def load_ambience(self, normalize=True):
+        return self.noise
+
+
+class SynScene:
+    def __init__(self, idx: int, spec: Optional[SceneSpec] = None):
+        import types
+        from collections import OrderedDict
+        spec = spec if spec is not None else c3_scene_spec(idx)
+        arrays, amb = host_scene_arrays(spec, dtype=np.float64)
+        rng = np.random.default_rng(idx)
+        self.duration, self.sample_rate, self.ref_db = spec.duration, spec.sr, spec.ref_db
+        evs = [SynEvent(f"event{k:03d}", x, spec.sr, e.n_irs, e.snr, min(e.start, spec.duration - len(x) / spec.sr - 0.2), rng)
+               for k, (e, (x, h)) in enumerate(zip(spec.events, arrays))]
+        self.events = OrderedDict((e.alias, e) for e in evs)
+        self.ambience = OrderedDict(amb=SynAmbience(amb, spec.ref_db)) if amb is not None else OrderedDict()
+        self.audio = OrderedDict()
+        irs = np.concatenate([h for _, h in arrays], axis=1)
+        self.state = types.SimpleNamespace(name="synthetic", microphones=OrderedDict(mic000=None), num_emitters=irs.shape[1],
+                                           simulate=lambda: None, get_irs=lambda: OrderedDict(mic000=irs))
+        self.index = idx
+
+    def get_events(self):
+        return list(self.events.values())
+
+    def to_dict(self):
+        return dict(index=self.index, duration=self.duration, events=list(self.events))

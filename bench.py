@@ -11,8 +11,9 @@ cross-fade, partitioned convolution, gains, mixdown) over the GPU's batch.
 
 Printed JSON (rank 0): `value` = whole-job scene-seconds/s with inputs resident in HBM; `e2e` = the same metric
 through the C-ABI with HOST (pinned) buffers, host<->device copies inside the timed region; `roofline` for the
-dominant kernel from CUDA events recorded on the render stream inside the timed region; `cpu_baseline` = the
-oracle port of the reference algorithm on the host cores (bounded, extrapolated sample).
+dominant kernel from CUDA events recorded on the render stream inside the timed region (plus the fp32 side of the
+roofline: the path sits at the fp32 ridge); `cpu_baseline` = the UNMODIFIED reference functions
+(baseline/_ref, see baseline/reference_arm.py) on the host cores, bounded sample.
 """
 from __future__ import annotations
 
@@ -119,27 +120,31 @@ def scene_spec(workload: str, idx: int):
 
 # ------------------------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU algorithm (oracle port; the reference is pure Python and cannot
-    travel to the GPU box) on the host cores, same metric/config; rank 0 only."""
+    """--impl reference: the reference's own CPU implementation (unmodified functions from baseline/_ref, driven by
+    baseline/reference_arm.py) on the host cores, same metric / config; rank 0 only. Each step is one bounded sample:
+    one scene per core. Steps stop early when the arm's time budget (~4 minutes) is used up; `steps` is what ran."""
     if rank != 0:
         return
-    from oracle import cpu_baseline
+    from baseline import reference_arm
     vals, last = [], None
     spent = 0.0
+    budget = float(os.environ.get("ALR_REFERENCE_BUDGET_S", "240"))
     for i in range(max(1, args.steps)):
-        last = cpu_baseline.run(n_workers=args.cpu_workers, first_scene=64 * i)
+        last = reference_arm.run(n_workers=args.cpu_workers, workload=args.workload, first_scene=64 * i)
         vals.append(last["value"])
         spent += last["wall_s"]
-        if spent + last["wall_s"] > 150:  # keep the whole arm within a few minutes
+        if spent + last["wall_s"] > budget:
             break
     value = sum(vals) / len(vals)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
-        "steps": len(vals), "warmup": 0, "ms_per_step": 1000.0 * last["wall_s"], "higher_is_better": True,
+        "steps": len(vals), "steps_requested": args.steps, "warmup": 0, "ms_per_step": 1000.0 * last["wall_s"],
+        "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args, world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"],
-                         "per_core": last["per_core"], "mean_scene_cpu_s": last["mean_scene_cpu_s"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"],
+                         "per_core": last["per_core"], "mean_scene_cpu_s": last["mean_scene_cpu_s"],
+                         "values_per_step": vals},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -147,9 +152,12 @@ def run_reference(args, rank, world):
 
 
 def partition_size():
+    """Partition length P the library is compiled with, read from the source (the reference arm must not load the
+    CUDA library just to fill in `config`)."""
+    import re
     try:
-        from audiblelight_b200 import _lib
-        return int(_lib.load().alr_partition_size())
+        src = open(os.path.join(ROOT, "audiblelight_b200", "csrc", "alr_fft.cuh")).read()
+        return int(re.search(r"#define\s+ALR_P\s+(\d+)", src).group(1))
     except Exception:
         return None
 
@@ -165,6 +173,30 @@ def config_dict(args, world):
             "scenes_total": args.scenes_per_gpu * world, "parallelism": f"scene-sharded x{world}, no collective",
             "cache": "inputs per step (>= 18 GB per GPU at 128 scenes) are far larger than the 126 MB L2",
             "partition": partition_size()}
+
+
+FP32_PEAK_TFLOPS = 69.8  # measured: plain FFMA, tools/micro/ffma2_bench.cu on B200 @ 1965 MHz (profiles/r01_ffma2.txt)
+
+
+def event_flops(job, P):
+    """fp32 flops of one event in the partitioned closed form the kernels implement: RIR partition
+    FFTs, source block FFTs, spectral multiply-accumulates (8 flops per complex MAC) and the inverse FFTs, with the
+    planner's own partition plan (alr_debug_plan; host only). A P-point complex FFT counts 5 P log2 P."""
+    import math
+    from audiblelight_b200.renderer import debug_plan
+    if job.irs is None:
+        return 0.0
+    C, N = int(job.n_channels), int(job.irs.shape[1])
+    plan = debug_plan(job)
+    K, B = plan["K"], plan["B_valid"]
+    f_fft = 5.0 * P * math.log2(P)
+    xb0, xnb = plan["irs"][:, 0], plan["irs"][:, 1]
+    pairs = 0
+    for l in range(N):
+        for k in range(K):
+            # source blocks j of IR l with output block xb0 + j + k inside the valid range
+            pairs += max(0, min(int(xnb[l]), B - int(xb0[l]) - k))
+    return (N * C * K + int(xnb.sum()) + B * C) * f_fft + 8.0 * P * C * pairs
 
 
 def main():
@@ -214,6 +246,7 @@ def main():
                    workspace_limit=None if args.workspace_mb is None else args.workspace_mb << 20)
     packed = rnd.pack(jobs, scenes)
     stream = torch.cuda.current_stream().cuda_stream
+    flops_step = sum(event_flops(j, partition_size() or 2048) for j in jobs) if rank == 0 else 0.0
 
     for _ in range(max(args.warmup, 3)):
         rnd.run(packed, stream)
@@ -306,6 +339,34 @@ def main():
                                "d2h_bytes_per_step": int(p["d2h_bytes"]),
                                "note": "mix-only: PCM_16 (T, C) of every scene mix is the only download"}
         del h_jobs, h_scenes
+        # What a user of install() gets: the reference's own objects in, results on the objects out. float64 RIRs in
+        # pageable numpy memory (as the reference's backends deliver them), converted to float32 by the host layer,
+        # every event's spatial audio and every mix copied back and stored on the Event / Scene objects
+        # (audiblelight_b200.synthesize.render_scenes == render_audio_for_all_scene_events + generate_scene_audio_from_events
+        # per scene). Informational; building the synthetic objects is not timed.
+        try:
+            from audiblelight_b200 import synthesize as syn
+            So = min(8, Se)
+            objs = [wl.SynScene(specs[i].index) for i in range(So)]
+            syn.render_scenes(objs, renderer=rnd, pinned=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                syn.render_scenes(objs, renderer=rnd, pinned=True)
+                p = rnd.profile()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            e2e["objects_mode"] = {"value": sum(o.duration for o in objs) * world * 2 / dt, "unit": UNIT,
+                                   "scenes_per_step_per_gpu": So, "h2d_bytes_per_step": int(p["h2d_bytes"]),
+                                   "d2h_bytes_per_step": int(p["d2h_bytes"]),
+                                   "note": "duck-typed Scene objects with float64 pageable RIRs -> render_scenes -> "
+                                           "event.spatial_audio (float64) + scene.audio on the objects"}
+            del objs
+        except Exception as exc:  # informational leg: never lose the headline over it
+            e2e["objects_mode"] = {"error": repr(exc)}
 
     if rank != 0:
         if world > 1:
@@ -353,10 +414,21 @@ def main():
                      "frac": b_alg / (ms_per_step / 1000.0) / 1e9 / peak,
                      "note": "whole hot path: B_alg of SURVEY.md 8(d) / step time"},
     }
+    # the fp32 side (report max(t_HBM, t_fp32) as the honest bound; no tensor cores on this path)
+    t_hbm_ms = b_alg / (peak * 1e9) * 1e3
+    t_fp32_ms = flops_step / (FP32_PEAK_TFLOPS * 1e12) * 1e3
+    roofline["fp32"] = {
+        "flops_per_step": flops_step, "achieved": flops_step / (ms_per_step / 1000.0) / 1e12, "peak": FP32_PEAK_TFLOPS,
+        "unit": "TFLOP/s", "frac": flops_step / (ms_per_step / 1000.0) / 1e12 / FP32_PEAK_TFLOPS,
+        "peak_source": "measured FFMA rate, tools/micro/ffma2_bench.cu (profiles/r01_ffma2.txt)",
+        "model": "partitioned closed form: (N C K + sum xnb + B C) 5 P log2 P + 8 P C (active X.H pairs), planner's plan"}
+    roofline["bound_times_ms"] = {"hbm": t_hbm_ms, "fp32": t_fp32_ms}
+    roofline["pipeline_bound"] = "fp32" if t_fp32_ms > t_hbm_ms else "hbm"
+    roofline["pipeline"]["frac_of_bound"] = max(t_hbm_ms, t_fp32_ms) / ms_per_step
     cpu = None
     if not args.no_cpu_baseline:
-        from oracle import cpu_baseline
-        c = cpu_baseline.run(n_workers=args.cpu_workers)
+        from baseline import reference_arm
+        c = reference_arm.run(n_workers=args.cpu_workers, workload=args.workload)
         cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"], "sample": c["sample"],
                "per_core": c["per_core"], "mean_scene_cpu_s": c["mean_scene_cpu_s"], "wall_s": c["wall_s"]}
     line = {
