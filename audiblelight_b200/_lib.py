@@ -58,6 +58,7 @@ SYMBOLS = [
     ("alr_create", C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     ("alr_destroy", None, [C.c_void_p]),
     ("alr_set_workspace_limit", C.c_int, [C.c_void_p, C.c_int64]),
+    ("alr_set_option", C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     ("alr_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("alr_render", C.c_int, [C.c_void_p, C.POINTER(AlrEvent), C.c_int64, C.POINTER(AlrScene), C.c_int64, C.c_int,
                              C.POINTER(AlrEventStats), C.c_void_p]),

@@ -106,6 +106,7 @@ struct alr_context {
   int lookahead = 2;                      // runs whose RIRs are produced ahead of the consumer tasks
   int fused_grid = 0;                     // resident CTAs of k_mov_fused (SMs x occupancy)
   int sm_clock_khz = 0;
+  int mix_group = 0;                      // scenes per ambience-reduction + mixdown group (0: all at once)
   HostBuf stage, stage_out, stage_aug;
   int64_t ws_limit = (int64_t)4 << 30;  // 4 GiB: 3 % faster than 2 GiB on the benchmark (fewer, fuller launches); 8 GiB adds 1 %
   int profiling = 0;
@@ -513,14 +514,28 @@ bool plan_fused(EvDev* evs, int ne, IrDev* irs, const int2* lr, long long ring_s
     const EvDev& d = evs[e];
     const int l = fo - d.fo0;
     const long long size = (long long)d.K * d.C;
-    if (head + size > ring_slots) head = 0;
+    const long long old_head = head;
+    const bool wrapped = head + size > ring_slots;
+    if (wrapped) head = 0;
     const long long lo = head, hi = head + size;
-    // previous occupants overlapping [lo, hi): a prefix of the live list (the ring is a FIFO)
+    // Previous occupants overlapping [lo, hi): a prefix of the live list (the ring is a FIFO). On a wrap the regions left
+    // behind in the abandoned tail [old_head, ring_slots) are the OLDEST live entries; they are released first although
+    // nothing overwrites them yet, otherwise they would sit in front of the entries at the start of the ring that the
+    // new region does overwrite (RIR sizes differ between events).
     int pop_lo = live_lo;
+    if (live_lo > 0 && !wrapped) {
+      // the last region released by the PREVIOUS allocation may straddle `lo` (RIR sizes differ between events): this
+      // producer overwrites its upper part and has to wait for its readers as well — the previous allocation's P-tasks
+      // do wait for them, but nothing orders those P-tasks before ours
+      const EvDev& o = evs[fo_ev[live_lo - 1]];
+      const long long olo = reg_lo[live_lo - 1], ohi = olo + (long long)o.K * o.C;
+      if (olo < hi && ohi > lo) pop_lo = live_lo - 1;
+    }
     while (live_lo < fo) {
       const EvDev& o = evs[fo_ev[live_lo]];
       const long long olo = reg_lo[live_lo], ohi = olo + (long long)o.K * o.C;
-      if (ohi <= lo || olo >= hi) break;
+      const bool in_tail = wrapped && olo >= old_head;
+      if (!in_tail && (ohi <= lo || olo >= hi)) break;
       // its readers must be in the queue before this producer
       while (c_emitted <= last_run[live_lo]) {
         if (runs[c_emitted].lmax >= 0 && evs[runs[c_emitted].ev].fo0 + runs[c_emitted].lmax >= fo) ok = false;
@@ -673,6 +688,7 @@ int alr_create(int device, alr_context** out) {
     if (const char* v = getenv("ALR_FUSED")) ctx->fused = fused_ok && atoi(v) != 0;
     if (const char* v = getenv("ALR_RING_MB")) ctx->ring_bytes = std::max<int64_t>(1, atoll(v)) << 20;
     if (const char* v = getenv("ALR_LOOKAHEAD")) ctx->lookahead = std::max(0, atoi(v));
+    if (const char* v = getenv("ALR_MIX_GROUP")) ctx->mix_group = std::max(0, atoi(v));
   }
   *out = ctx;
   return ALR_OK;
@@ -707,6 +723,27 @@ void alr_destroy(alr_context* ctx) {
 int alr_set_workspace_limit(alr_context* ctx, int64_t bytes) {
   if (!ctx || bytes < (1 << 16)) return fail(ALR_ERR_INVALID, "alr_set_workspace_limit: bad argument");
   ctx->ws_limit = bytes;
+  return ALR_OK;
+}
+
+int alr_set_option(alr_context* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return fail(ALR_ERR_INVALID, "alr_set_option: bad argument");
+  const std::string n(name);
+  if (n == "fused") {
+    if (value && ctx->fused_grid <= 0) return fail(ALR_ERR_INVALID, "alr_set_option: the fused launch is not available on this device");
+    ctx->fused = value != 0;
+  } else if (n == "ring_bytes") {
+    if (value < (1 << 20)) return fail(ALR_ERR_INVALID, "alr_set_option: ring_bytes must be >= 1 MiB");
+    ctx->ring_bytes = value;
+  } else if (n == "lookahead") {
+    if (value < 0 || value > 1024) return fail(ALR_ERR_INVALID, "alr_set_option: lookahead out of range");
+    ctx->lookahead = (int)value;
+  } else if (n == "mix_group") {
+    if (value < 0) return fail(ALR_ERR_INVALID, "alr_set_option: mix_group must be >= 0");
+    ctx->mix_group = (int)value;
+  } else {
+    return fail(ALR_ERR_INVALID, "alr_set_option: unknown option '%s'", name);
+  }
   return ALR_OK;
 }
 
@@ -1305,26 +1342,32 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       int rc = upload_mix_desc(st);
       if (rc) return rc;
     }
-    const int a0 = h_scenes[s0].amb0;
-    const int a1 = h_scenes[s1 - 1].amb0 + h_scenes[s1 - 1].n_amb;
-    for (int a = a0; a < a1; a += 32768) {
-      const int cnt = std::min(32768, a1 - a);
-      k_amb_partial<<<dim3(kAmbSlices, cnt), 256, 0, st>>>(d_ambs + a, d_ambparts);
-      LAUNCH_CHECK(kCatMix);
-    }
-    if (a1 > a0) {
-      k_amb_final<<<ceil_div((long long)(a1 - a0) * 32, 128), 128, 0, st>>>(d_ambs + a0, a1 - a0, d_ambparts);
-      LAUNCH_CHECK(kCatMix);
-    }
-    long long max_t = 0;
-    for (int sidx = s0; sidx < s1; ++sidx) max_t = std::max(max_t, h_scenes[sidx].T);
-    for (int sidx = s0; sidx < s1; sidx += 32768) {
-      const int cnt = std::min(32768, s1 - sidx);
-      k_mix<<<dim3(ceil_div(max_t, 1024), cnt), 256, 0, st>>>(d_scenes + sidx, d_ambs, d_mevs);
-      LAUNCH_CHECK(kCatMix);
-      if (any_pcm) {
-        k_pcm16<<<dim3(ceil_div(max_t, 256), cnt), 256, 0, st>>>(d_scenes + sidx);
+    // Groups of `mix_group` scenes: the ambience of a group (23 MB per one-minute 4-channel layer) is reduced and then
+    // mixed right away, so that the mixdown's second read of it can hit the 126 MB L2 (profiles/r02_mix_group.txt).
+    const int G = ctx->mix_group > 0 ? ctx->mix_group : (s1 - s0);
+    for (int g0 = s0; g0 < s1; g0 += G) {
+      const int g1 = std::min(g0 + G, s1);
+      const int a0 = h_scenes[g0].amb0;
+      const int a1 = h_scenes[g1 - 1].amb0 + h_scenes[g1 - 1].n_amb;
+      for (int a = a0; a < a1; a += 32768) {
+        const int cnt = std::min(32768, a1 - a);
+        k_amb_partial<<<dim3(kAmbSlices, cnt), 256, 0, st>>>(d_ambs + a, d_ambparts);
         LAUNCH_CHECK(kCatMix);
+      }
+      if (a1 > a0) {
+        k_amb_final<<<ceil_div((long long)(a1 - a0) * 32, 128), 128, 0, st>>>(d_ambs + a0, a1 - a0, d_ambparts);
+        LAUNCH_CHECK(kCatMix);
+      }
+      long long max_t = 0;
+      for (int sidx = g0; sidx < g1; ++sidx) max_t = std::max(max_t, h_scenes[sidx].T);
+      for (int sidx = g0; sidx < g1; sidx += 32768) {
+        const int cnt = std::min(32768, g1 - sidx);
+        k_mix<<<dim3(ceil_div(max_t, 1024), cnt), 256, 0, st>>>(d_scenes + sidx, d_ambs, d_mevs);
+        LAUNCH_CHECK(kCatMix);
+        if (any_pcm) {
+          k_pcm16<<<dim3(ceil_div(max_t, 256), cnt), 256, 0, st>>>(d_scenes + sidx);
+          LAUNCH_CHECK(kCatMix);
+        }
       }
     }
     if (host_mode) {

@@ -177,7 +177,7 @@ class PinnedPool:
 class Renderer:
     """One context per GPU (alr_create). Not thread-safe; calls block until results are ready."""
 
-    def __init__(self, device: int = -1, workspace_limit: Optional[int] = None, profiling: bool = False):
+    def __init__(self, device: int = -1, workspace_limit: Optional[int] = None, profiling: bool = False, **options):
         self._lib = _lib.load()
         h = C.c_void_p()
         _lib.check(self._lib.alr_create(int(device), C.byref(h)))
@@ -187,6 +187,8 @@ class Renderer:
             _lib.check(self._lib.alr_set_workspace_limit(self._h, int(workspace_limit)))
         if profiling:
             _lib.check(self._lib.alr_set_profiling(self._h, 1))
+        for name, value in options.items():  # alr_set_option switches: fused=1, ring_bytes=..., lookahead=..., mix_group=...
+            self.set_option(name, value)
         self.pool = PinnedPool(self._lib, self._h)
 
     def close(self):
@@ -201,6 +203,9 @@ class Renderer:
             self.close()
         except Exception:
             pass
+
+    def set_option(self, name: str, value: int):
+        _lib.check(self._lib.alr_set_option(self._h, name.encode(), int(value)))
 
     def set_profiling(self, enable: bool):
         _lib.check(self._lib.alr_set_profiling(self._h, 1 if enable else 0))

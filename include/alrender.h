@@ -190,6 +190,14 @@ void alr_destroy(alr_context* ctx);
 
 /* Upper bound for the spectra workspace (bytes); work is cut into chunks that fit. Default 4 GiB (device inputs; host inputs use at most 512 MiB so that transfers pipeline). */
 int alr_set_workspace_limit(alr_context* ctx, int64_t bytes);
+/* Tuning switches (name, value); unknown names fail with ALR_ERR_INVALID.
+ *   "fused"       1: moving events go through the persistent producer/consumer launch k_mov_fused (RIR spectra handed
+ *                 from FFT tasks to multiply-accumulate tasks through an L2-resident ring); 0 (default): k_ir_fft + k_cmac
+ *   "ring_bytes"  size of that ring (default 64 MiB)
+ *   "lookahead"   runs of output blocks whose RIR spectra are produced ahead of their consumers (default 2)
+ *   "mix_group"   scenes per ambience-reduction + mixdown launch group, sized so that a group's ambience stays in L2
+ *                 between the two passes; 0 = all scenes in one group */
+int alr_set_option(alr_context* ctx, const char* name, int64_t value);
 /* 1: record per-kernel CUDA-event timings into alr_profile (adds event records, no syncs). Default 0. */
 int alr_set_profiling(alr_context* ctx, int enable);
 
