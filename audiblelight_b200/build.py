@@ -6,7 +6,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "csrc", "alrender.cu")
 _DEPS = [_SRC, os.path.join(_HERE, "csrc", "alr_kernels.cuh"), os.path.join(_HERE, "csrc", "alr_fft.cuh"),
-         os.path.join(_HERE, "csrc", "alr_fused.cuh"),
+         os.path.join(_HERE, "csrc", "alr_fused.cuh"), os.path.join(_HERE, "csrc", "alr_sweep.cuh"),
          os.path.join(os.path.dirname(_HERE), "include", "alrender.h")]
 _LIB = os.path.join(_HERE, "libalrender.so")
 

@@ -19,6 +19,7 @@
 #include "../../include/alrender.h"
 #include "alr_kernels.cuh"
 #include "alr_fused.cuh"
+#include "alr_sweep.cuh"
 
 using namespace alr;
 
@@ -101,12 +102,16 @@ struct alr_context {
   float* d_win = nullptr;  // sin^2(pi p / 256), p < 128
   DevBuf spec, desc, misc, arena, augbuf, augdesc, ring;
   // persistent producer/consumer launch for moving events (alr_fused.cuh)
-  int fused = 0;                          // ALR_FUSED=1: moving events through k_mov_fused (experiment, see profiles/r02_fused_ring.txt)
+  int fused = 0;                          // moving events: 0 = k_ir_fft + k_cmac, 1 = k_mov_fused (alr_fused.cuh, experiment,
+                                          // profiles/r02_fused_ring.txt), 2 = k_mov_sweep (alr_sweep.cuh)
+  int sweep_grid = 0;                     // CTAs of k_mov_sweep (one per SM), 0: not available
   int64_t ring_bytes = (int64_t)64 << 20; // H-spectra ring (must stay L2 resident: 126 MB on B200)
   int lookahead = 2;                      // runs whose RIRs are produced ahead of the consumer tasks
   int fused_grid = 0;                     // resident CTAs of k_mov_fused (SMs x occupancy)
   int sm_clock_khz = 0;
   int mix_group = 0;                      // scenes per ambience-reduction + mixdown group (0: all at once)
+  int64_t l2_persist_bytes = 0;           // L2 set aside for persisting lines (the ring of k_mov_sweep); 0: off
+  int64_t l2_window_max = 0;
   HostBuf stage, stage_out, stage_aug;
   int64_t ws_limit = (int64_t)4 << 30;  // 4 GiB: 3 % faster than 2 GiB on the benchmark (fewer, fuller launches); 8 GiB adds 1 %
   int profiling = 0;
@@ -133,6 +138,7 @@ constexpr int kTileSlices = 8;
 constexpr int kGainSlices = 64;
 constexpr int kAmbSlices = 64;
 
+constexpr int kMaxSweepSlots = 64;  // sweeper slots of k_mov_sweep (SMs / 8 bin slices)
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -155,12 +161,12 @@ struct EvSize {
   int n_irfft = 0, n_cmac = 0, n_cmac_static = 0, n_ifft = 0, n_parts = 0;
   bool pass = false;
   // moving events taken by k_mov_fused: H lives in the ring (z.h_ws = 0), tasks instead of k_ir_fft / k_cmac CTAs
-  bool fused = false;
+  int fused = 0;       // 0 / 1 (k_mov_fused) / 2 (k_mov_sweep)
   long long h_ws = 0;  // H slots in the chunk workspace
   int n_ptask = 0, n_ctask = 0;
 };
 
-int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0) {
+int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0, int mover = 0) {
   z = EvSize();
   if (u.n_channels < 1) return fail(ALR_ERR_INVALID, "event %d: n_channels must be >= 1", idx);
   if (u.n_out < 1 || !u.spatial) return fail(ALR_ERR_INVALID, "event %d: no output buffer", idx);
@@ -224,7 +230,9 @@ int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0)
           le[l] = (int)((t_hi - 1) / kP);
         }
       }
-      int wmax = 0, lmin = 0;
+      int wmax = 0, lmin = 0, xnb_max = 0;
+      for (int l = 0; l < N; ++l)
+        if (fb[l] >= 0) xnb_max = std::max(xnb_max, le[l] - fb[l] + 1);
       for (int b0 = 0; b0 < z.B_valid; b0 += kGm) {
         const int b1 = std::min(b0 + kGm, z.B_valid) - 1;
         while (lmin < N && (fb[lmin] < 0 || le[lmin] + z.K - 1 < b0)) ++lmin;
@@ -234,7 +242,14 @@ int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0)
         wmax = std::max(wmax, lmax - lmin + 1);
       }
       const long long ir_slots = (long long)z.K * C;
-      z.fused = (long long)(wmax + 2) * ir_slots <= ring_slots;
+      if (mover == 1) {
+        z.fused = (long long)(wmax + 2) * ir_slots <= ring_slots ? 1 : 0;
+      } else if (mover == 2) {
+        // k_mov_sweep: one capsule group, the RIR's output span fits the accumulator window, its source blocks fit the
+        // register FIR, and the ring holds a few RIRs for every sweeper slot
+        z.fused = (C <= kChanGroup && xnb_max >= 1 && xnb_max <= kSwMaxXnb && z.K + xnb_max - 1 <= kSwW &&
+                   64 * ir_slots <= ring_slots) ? 2 : 0;
+      }
     }
   }
   const int ncg = (C + kChanGroup - 1) / kChanGroup;
@@ -246,11 +261,11 @@ int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0)
   z.n_irfft = (int)z.h;
   z.n_cmac = moving ? (int)n_cmac : 0;         // generic kernel: moving events
   if (z.fused) {
-    if ((long long)N * C > 0x3ffffff0LL) z.fused = false;
+    if ((long long)N * C * kSwKSplit > 0x3ffffff0LL) z.fused = 0;
   }
   if (z.fused) {
-    z.n_ptask = N * C;
-    z.n_ctask = (int)n_cmac;
+    z.n_ptask = N * C * (z.fused == 2 ? kSwKSplit : 1);
+    z.n_ctask = z.fused == 1 ? (int)n_cmac : 0;
     z.h_ws = 0;
     z.n_irfft = 0;
     z.n_cmac = 0;
@@ -379,9 +394,9 @@ struct Chunk {
   size_t base = 0;   // offset of the blob in the staging / descriptor buffers
   int part_base = 0, ir_base = 0, gain_base = 0;
   // fused launch: RIRs, tasks and (RIR, capsule) energy entries of the chunk's fused events
-  int n_fo = 0, n_tasks = 0;
+  int n_fo = 0, n_tasks = 0, n_sweep_ev = 0;
   long long n_ecap = 0;
-  size_t off_tasks = 0, off_pop = 0, off_ncons = 0;
+  size_t off_tasks = 0, off_pop = 0, off_ncons = 0, off_prod = 0, off_slotoff = 0, off_slotjobs = 0;
 };
 
 void layout_chunk(Chunk& ch) {
@@ -407,6 +422,9 @@ void layout_chunk(Chunk& ch) {
   ch.off_tasks = take((size_t)ch.n_tasks * sizeof(FusedTask));
   ch.off_pop = take((size_t)ch.n_fo * sizeof(int2));
   ch.off_ncons = take((size_t)ch.n_fo * sizeof(int2));
+  ch.off_prod = take((size_t)ch.n_fo * sizeof(int));
+  ch.off_slotoff = take((size_t)(kMaxSweepSlots + 1) * sizeof(int));
+  ch.off_slotjobs = take((size_t)ch.n_sweep_ev * sizeof(int));
   ch.bytes = align_up(o, 256);
 }
 
@@ -426,6 +444,7 @@ void make_chunks(const std::vector<EvSize>& sz, int64_t ws_limit, std::vector<Ch
       if (e > ch.ev_begin && z.fused && (long long)ch.n_tasks + z.n_ptask + z.n_ctask > 0x3ffffff0LL) break;
       bytes += add;
       ch.hslots += z.h_ws;
+      if (z.fused == 2) ch.n_sweep_ev += 1;
       if (z.fused) {
         ch.n_fo += z.n_ir;
         ch.n_tasks += z.n_ptask + z.n_ctask;
@@ -564,6 +583,95 @@ bool plan_fused(EvDev* evs, int ne, IrDev* irs, const int2* lr, long long ring_s
   return ok && nt == n_tasks_expected;
 }
 
+// ---- production order of the sweep launch ------------------------------------------------------------------------------
+// k_mov_sweep (alr_sweep.cuh): the chunk's sweep events are dealt to `n_slots` sweeper slots (8 CTAs each, one per
+// 256-bin slice; greedy by RIR count), every slot walks its events' RIRs in order, and all slots advance at the same
+// rate. The producers therefore make "RIR t of every slot" for t = 0, 1, 2, ...: that production order is the ticket
+// order of the P-tasks and the allocation order of the ring, so whatever a producer overwrites was produced about one
+// ring-full earlier and has long been consumed.
+//   prod[p]  ordinal (event-major: ev.fo0 + l) of the p-th RIR produced
+//   pop[fo]  production indices [x, y) whose ring regions RIR fo overwrites (wait for ready + consumed of prod[x..y))
+bool plan_sweep(EvDev* evs, int ne, IrDev* irs, long long ring_slots, int n_slots_max, FusedTask* tasks,
+                int n_tasks_expected, int2* pop, int2* need, int* prod, int n_fo_expected, int* slot_off, int* slot_jobs,
+                int n_ev_expected, int* n_slots_out) {
+  static thread_local std::vector<int> sweep_ev, load, cur_job, cur_l;
+  static thread_local std::vector<std::vector<int>> jobs;
+  sweep_ev.clear();
+  int n_fo = 0;
+  for (int e = 0; e < ne; ++e)
+    if (evs[e].fused == 2) {
+      evs[e].fo0 = n_fo;
+      n_fo += evs[e].N;
+      sweep_ev.push_back(e);
+    }
+  if (n_fo != n_fo_expected || (int)sweep_ev.size() != n_ev_expected) return false;
+  const int n_slots = std::max(1, std::min<int>(n_slots_max, (int)sweep_ev.size()));
+  jobs.assign(n_slots, {});
+  load.assign(n_slots, 0);
+  for (int e : sweep_ev) {  // in event order, to the least loaded slot
+    int best = 0;
+    for (int s2 = 1; s2 < n_slots; ++s2)
+      if (load[s2] < load[best]) best = s2;
+    jobs[best].push_back(e);
+    load[best] += evs[e].N;
+  }
+  int nj = 0;
+  for (int s2 = 0; s2 < n_slots; ++s2) {
+    slot_off[s2] = nj;
+    for (int e : jobs[s2]) slot_jobs[nj++] = e;
+  }
+  for (int s2 = n_slots; s2 <= kMaxSweepSlots; ++s2) slot_off[s2] = nj;
+  *n_slots_out = n_slots;
+  for (int e : sweep_ev)
+    for (int l = 0; l < evs[e].N; ++l)
+      need[evs[e].fo0 + l] = make_int2(kSwBinCtas * (kSwSweepThreads / 32), evs[e].C * kSwKSplit + 1);
+  // production order + ring allocation (FIFO; see plan_fused for the wrap / straddle rules)
+  cur_job.assign(n_slots, 0);
+  cur_l.assign(n_slots, 0);
+  static thread_local std::vector<long long> reg_lo, reg_hi;  // ring region per production index
+  reg_lo.resize(n_fo);
+  reg_hi.resize(n_fo);
+  long long head = 0;
+  int live_lo = 0, p = 0, nt = 0;
+  bool any = true;
+  while (any) {
+    any = false;
+    for (int s2 = 0; s2 < n_slots; ++s2) {
+      while (cur_job[s2] < (int)jobs[s2].size() && cur_l[s2] >= evs[jobs[s2][cur_job[s2]]].N) {
+        ++cur_job[s2];
+        cur_l[s2] = 0;
+      }
+      if (cur_job[s2] >= (int)jobs[s2].size()) continue;
+      any = true;
+      const int e = jobs[s2][cur_job[s2]], l = cur_l[s2]++;
+      const EvDev& d = evs[e];
+      const long long size = (long long)d.K * d.C;
+      if (size > ring_slots) return false;
+      const long long old_head = head;
+      const bool wrapped = head + size > ring_slots;
+      if (wrapped) head = 0;
+      const long long lo = head, hi = head + size;
+      int pop_lo = live_lo;
+      if (live_lo > 0 && !wrapped && reg_lo[live_lo - 1] < hi && reg_hi[live_lo - 1] > lo) pop_lo = live_lo - 1;
+      while (live_lo < p) {
+        const bool in_tail = wrapped && reg_lo[live_lo] >= old_head;
+        if (!in_tail && (reg_hi[live_lo] <= lo || reg_lo[live_lo] >= hi)) break;
+        ++live_lo;
+      }
+      reg_lo[p] = lo;
+      reg_hi[p] = hi;
+      head = hi;
+      const int fo = d.fo0 + l;
+      irs[d.ir0 + l].hring = (int)lo;
+      pop[fo] = make_int2(pop_lo, live_lo);
+      prod[p] = fo;
+      for (int c = 0; c < d.C * kSwKSplit; ++c) tasks[nt++] = FusedTask{kTaskP, e, l, c};  // sub = capsule * kSwKSplit + part
+      ++p;
+    }
+  }
+  return p == n_fo && nt == n_tasks_expected;
+}
+
 // ---- profiling helpers ---------------------------------------------------------------------------------------
 int prof_mark(alr_context* ctx, cudaStream_t st, int cat) {
   ctx->prof.kernel_launches += (cat >= 0 && cat != kNumCat) ? 1 : 0;
@@ -684,8 +792,35 @@ int alr_create(int device, alr_context** out) {
       ctx->fused_grid = sms * per_sm;
       ctx->sm_clock_khz = std::max(khz, 500000);
     }
-    const bool fused_ok = ctx->fused_grid > 0;
-    if (const char* v = getenv("ALR_FUSED")) ctx->fused = fused_ok && atoi(v) != 0;
+    {
+      int per_sm2 = 0;
+      cudaError_t s1 = cudaFuncSetAttribute(k_mov_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSmem);
+      cudaError_t s2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_mov_sweep, kSwThreads, kSwSmem);
+      if (s1 == cudaSuccess && s2 == cudaSuccess && per_sm2 >= 1 && sms >= kSwBinCtas) ctx->sweep_grid = sms;
+      else cudaGetLastError();
+    }
+    // Experiment (ALR_L2_PERSIST=1, off): pin the ring with a persisting access-policy window. Measured: k_mov_sweep
+    // unchanged (13.06 vs 13.10 ms per benchmark step) while every OTHER kernel of the step got slower with 72 MB of L2
+    // set aside (step 23.3 -> 26.7 ms), profiles/r02_sweep_tuning.txt.
+    if (ctx->sweep_grid > 0 && getenv("ALR_L2_PERSIST") && atoi(getenv("ALR_L2_PERSIST")) != 0) {
+      int max_persist = 0, max_window = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+      if (max_persist > 0 && max_window > 0) {
+        const size_t want = std::min<size_t>((size_t)max_persist, (size_t)ctx->ring_bytes + ((size_t)8 << 20));
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+          ctx->l2_persist_bytes = (int64_t)want;
+          ctx->l2_window_max = max_window;
+        } else {
+          cudaGetLastError();
+        }
+      }
+    }
+    if (getenv("ALR_TRACE")) fprintf(stderr, "[alr] L2 persisting %lld bytes, window max %lld\n", (long long)ctx->l2_persist_bytes, (long long)ctx->l2_window_max);
+    if (const char* v = getenv("ALR_FUSED")) {
+      const int m = atoi(v);
+      ctx->fused = (m == 1 && ctx->fused_grid > 0) ? 1 : (m == 2 && ctx->sweep_grid > 0) ? 2 : 0;
+    }
     if (const char* v = getenv("ALR_RING_MB")) ctx->ring_bytes = std::max<int64_t>(1, atoll(v)) << 20;
     if (const char* v = getenv("ALR_LOOKAHEAD")) ctx->lookahead = std::max(0, atoi(v));
     if (const char* v = getenv("ALR_MIX_GROUP")) ctx->mix_group = std::max(0, atoi(v));
@@ -730,8 +865,10 @@ int alr_set_option(alr_context* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return fail(ALR_ERR_INVALID, "alr_set_option: bad argument");
   const std::string n(name);
   if (n == "fused") {
-    if (value && ctx->fused_grid <= 0) return fail(ALR_ERR_INVALID, "alr_set_option: the fused launch is not available on this device");
-    ctx->fused = value != 0;
+    if (value < 0 || value > 2) return fail(ALR_ERR_INVALID, "alr_set_option: fused must be 0, 1 or 2");
+    if ((value == 1 && ctx->fused_grid <= 0) || (value == 2 && ctx->sweep_grid <= 0))
+      return fail(ALR_ERR_INVALID, "alr_set_option: that launch is not available on this device");
+    ctx->fused = (int)value;
   } else if (n == "ring_bytes") {
     if (value < (1 << 20)) return fail(ALR_ERR_INVALID, "alr_set_option: ring_bytes must be >= 1 MiB");
     ctx->ring_bytes = value;
@@ -1056,7 +1193,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     const auto& evl = *phase_events[ph];
     sizes[ph].resize(evl.size());
     for (size_t i = 0; i < evl.size(); ++i) {
-      int rc = size_event(evl[i], ph == 0 ? (int)i : dry_parent[i], sizes[ph][i], ph == 0 ? ring_slots : 0);
+      int rc = size_event(evl[i], ph == 0 ? (int)i : dry_parent[i], sizes[ph][i], ph == 0 ? ring_slots : 0, ctx->fused);
       if (rc) return rc;
     }
     // host mode: smaller chunks give the upload / compute / download pipeline something to overlap
@@ -1518,7 +1655,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         d.part0 = parts;
         d.nparts = z.n_parts;
         if (z.fused) {
-          d.fused = 1;
+          d.fused = z.fused;
           d.ecap0 = ecap_off;
           ecap_off += z.n_ptask;
         }
@@ -1537,10 +1674,17 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         p_ifft[i + 1] = p_ifft[i] + z.n_ifft;
         if (!z.pass && d.N == 0) l_tile[n_tile++] = i;
       }
-      if (ch.n_tasks > 0 &&
+      int n_sweep_slots = 0;
+      if (ch.n_tasks > 0 && ch.n_sweep_ev == 0 &&
           !plan_fused(h_evs, ne, h_irs, h_lr, ring_slots, ctx->lookahead, (FusedTask*)(hb + ch.off_tasks), ch.n_tasks,
                       (int2*)(hb + ch.off_pop), (int2*)(hb + ch.off_ncons), ch.n_fo))
         return fail(ALR_ERR_INVALID, "internal: inconsistent task plan for the fused launch");
+      if (ch.n_sweep_ev > 0 &&
+          !plan_sweep(h_evs, ne, h_irs, ring_slots, std::min(kMaxSweepSlots, ctx->sweep_grid / kSwBinCtas),
+                      (FusedTask*)(hb + ch.off_tasks), ch.n_tasks, (int2*)(hb + ch.off_pop), (int2*)(hb + ch.off_ncons),
+                      (int*)(hb + ch.off_prod), ch.n_fo, (int*)(hb + ch.off_slotoff), (int*)(hb + ch.off_slotjobs),
+                      ch.n_sweep_ev, &n_sweep_slots))
+        return fail(ALR_ERR_INVALID, "internal: inconsistent production plan for the sweep launch");
       host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
       // Descriptors. In host mode they travel on the UPLOAD stream, right behind this chunk's inputs and ahead of the
       // next chunk's: a copy on the compute stream would sit behind everything already queued on the H2D copy
@@ -1587,7 +1731,54 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
                                                                        ctx->d_win, d_xspec);
         LAUNCH_CHECK(kCatXFft);
       }
-      if (ch.n_tasks > 0) {
+      if (ch.n_sweep_ev > 0) {
+        CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)ch.n_fo * 2 * sizeof(int), st));
+        CUDA_TRY(cudaMemsetAsync(&d_ctl->ticket, 0, sizeof(int), st));
+        SweepArgs sa;
+        sa.evs = c_evs;
+        sa.irs = c_irs;
+        sa.tasks = (const FusedTask*)(db + ch.off_tasks);
+        sa.n_tasks = ch.n_tasks;
+        sa.pop = (const int2*)(db + ch.off_pop);
+        sa.need = (const int2*)(db + ch.off_ncons);
+        sa.prod = (const int*)(db + ch.off_prod);
+        sa.slot_off = (const int*)(db + ch.off_slotoff);
+        sa.slot_jobs = (const int*)(db + ch.off_slotjobs);
+        sa.n_slots = n_sweep_slots;
+        sa.ctl = d_ctl;
+        sa.ready = d_flags;
+        sa.consumed = d_flags + ch.n_fo;
+        sa.ecap = d_ecap;
+        sa.irscale = c_irscale;
+        sa.stats = d_stats;
+        sa.tw = ctx->d_tw;
+        sa.zeta = ctx->d_zeta;
+        sa.xspec = d_xspec;
+        sa.hring = (float2*)ctx->ring.p;
+        sa.yspec = d_yspec;
+        sa.spin_limit = (long long)ctx->sm_clock_khz * 2000LL;
+        // Pin the ring in L2 for this launch: the taps (9 GB per benchmark step), X and Y stream through the same cache and
+        // would otherwise push ring lines out between a producer's store and the sweepers' reads (56 % hit rate and 5 GB of
+        // ring write-backs per launch without this, profiles/r02_sweep_v1.txt).
+        if (ctx->l2_persist_bytes > 0) {
+          cudaStreamAttrValue av;
+          memset(&av, 0, sizeof(av));
+          av.accessPolicyWindow.base_ptr = ctx->ring.p;
+          av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)ctx->ring_bytes, (size_t)ctx->l2_window_max);
+          av.accessPolicyWindow.hitRatio = std::min(1.0f, (float)ctx->l2_persist_bytes / (float)av.accessPolicyWindow.num_bytes);
+          av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+          av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+          CUDA_TRY(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+        }
+        k_mov_sweep<<<ctx->sweep_grid, kSwThreads, kSwSmem, st>>>(sa);
+        LAUNCH_CHECK(kCatFused);
+        if (ctx->l2_persist_bytes > 0) {
+          cudaStreamAttrValue av;
+          memset(&av, 0, sizeof(av));
+          av.accessPolicyWindow.num_bytes = 0;
+          CUDA_TRY(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+        }
+      } else if (ch.n_tasks > 0) {
         CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)ch.n_fo * 2 * sizeof(int), st));
         CUDA_TRY(cudaMemsetAsync(&d_ctl->ticket, 0, sizeof(int), st));
         FusedArgs fa;

@@ -428,7 +428,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         from baseline import reference_arm
-        c = reference_arm.run(n_workers=args.cpu_workers, workload=args.workload)
+        c = reference_arm.run(n_workers=args.cpu_workers, workload=args.workload, select="cheapest")
         cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"], "sample": c["sample"],
                "per_core": c["per_core"], "mean_scene_cpu_s": c["mean_scene_cpu_s"], "wall_s": c["wall_s"]}
     line = {

@@ -191,8 +191,11 @@ void alr_destroy(alr_context* ctx);
 /* Upper bound for the spectra workspace (bytes); work is cut into chunks that fit. Default 4 GiB (device inputs; host inputs use at most 512 MiB so that transfers pipeline). */
 int alr_set_workspace_limit(alr_context* ctx, int64_t bytes);
 /* Tuning switches (name, value); unknown names fail with ALR_ERR_INVALID.
- *   "fused"       1: moving events go through the persistent producer/consumer launch k_mov_fused (RIR spectra handed
- *                 from FFT tasks to multiply-accumulate tasks through an L2-resident ring); 0 (default): k_ir_fft + k_cmac
+ *   "fused"       how moving events are rendered. 0: k_ir_fft + k_ir_scale + k_cmac (RIR spectra through HBM);
+ *                 1: k_mov_fused, persistent launch with FFT tasks and output-stationary multiply-accumulate tasks
+ *                 exchanging the spectra through a ring (experiment: loses, profiles/r02_fused_ring.txt);
+ *                 2: k_mov_sweep, warp-specialised persistent kernel (FFT producer warps, a TMA copy warp and
+ *                 input-driven sweeper warps with shared-memory accumulators), spectra stay in an L2-resident ring
  *   "ring_bytes"  size of that ring (default 64 MiB)
  *   "lookahead"   runs of output blocks whose RIR spectra are produced ahead of their consumers (default 2)
  *   "mix_group"   scenes per ambience-reduction + mixdown launch group, sized so that a group's ambience stays in L2

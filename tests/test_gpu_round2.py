@@ -144,10 +144,10 @@ def test_fifty_repeats_are_bit_identical(rnd):
             assert j.stats["gain"] == g
 
 
-# ---- the persistent producer/consumer launch (alr_set_option "fused") ------------------------------------------------------
-@pytest.fixture(scope="module")
-def rnd_fused():
-    r = Renderer(0, fused=1)
+# ---- the persistent launches for moving events (alr_set_option "fused": 1 = k_mov_fused, 2 = k_mov_sweep) -------------------
+@pytest.fixture(scope="module", params=[1, 2], ids=["ring", "sweep"])
+def rnd_fused(request):
+    r = Renderer(0, fused=request.param)
     yield r
     r.close()
 
@@ -169,8 +169,9 @@ def test_fused_launch_matches_oracle_on_a_moving_scene(rnd_fused, rnd):
     assert np.abs(sj.mix - sj2.mix).max() <= 1e-6
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["ring", "sweep"])
 @pytest.mark.parametrize("ring_mb,lookahead", [(2, 0), (3, 1), (8, 4), (64, 2)])
-def test_fused_launch_tight_rings_and_lookaheads(ring_mb, lookahead):
+def test_fused_launch_tight_rings_and_lookaheads(ring_mb, lookahead, mode):
     """Small rings force the planner to shrink the lookahead on the spot, make producers wait for consumers and push
     events that do not fit back to the unfused kernels; results must not depend on any of it."""
     rng = np.random.default_rng(21)
@@ -182,7 +183,7 @@ def test_fused_launch_tight_rings_and_lookaheads(ring_mb, lookahead):
             j = EventJob(audio=x, irs=h, n_channels=4, snr=8.0 + i, ref_db=-65.0)
             j.ir_frames, j.n_frames = moving_frames(lx / 24000.0, 24000.0, n, lx)
             lst.append(j)
-    r = Renderer(0, fused=1, ring_bytes=ring_mb << 20, lookahead=lookahead)
+    r = Renderer(0, fused=mode, ring_bytes=ring_mb << 20, lookahead=lookahead)
     r.render(jobs)
     first = [j.spatial.copy() for j in jobs]
     r.render(jobs)
