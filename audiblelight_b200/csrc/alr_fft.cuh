@@ -363,4 +363,34 @@ __device__ __forceinline__ void inv_block_from_global(const float2* __restrict__
   group_sync(bar);
 }
 
+// Register-to-register variants (k_small_rir keeps the RIR spectrum and every intermediate spectrum in registers):
+// forward: real samples a[r] -> spectrum o[m][k] (element t + kGroup m + 256 k); ends with a group barrier.
+__device__ __forceinline__ void fwd_block_to_regs(const float (&a)[16], float2 zt, FftSmem& s, const float2* __restrict__ tw,
+                                                  int t, int bar, float2 (&o)[kM3][kR3]) {
+  float2 v[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const float2 z = (r == 0) ? zt : cmul(zt, zeta_step(r));
+    v[r] = make_float2(a[r] * z.x, a[r] * z.y);
+  }
+  fft_core<false>(v, s, tw, t, bar, o);
+  group_sync(bar);
+}
+// inverse: spectrum v[r] (element t + kGroup r) -> o[m][k] = un-normalised (block sample e, overlap-tail sample P + e),
+// e = t + kGroup m + 256 k; ends with a group barrier.
+__device__ __forceinline__ void inv_block_from_regs(float2 (&v)[16], float2 zt, FftSmem& s, const float2* __restrict__ tw,
+                                                    int t, int bar, float2 (&o)[kM3][kR3]) {
+  fft_core<true>(v, s, tw, t, bar, o);
+  const float2 ztc = cconj(zt);
+#pragma unroll
+  for (int m = 0; m < kM3; ++m)
+#pragma unroll
+    for (int k = 0; k < kR3; ++k) {
+      const int r = m + (256 / kGroup) * k;  // e = t + kGroup r
+      const float2 z = (r == 0) ? ztc : cmul(ztc, cconj(zeta_step(r)));
+      o[m][k] = cmul(o[m][k], z);
+    }
+  group_sync(bar);
+}
+
 }  // namespace alr

@@ -65,7 +65,8 @@ struct EvDev {
   const float* xnorm;    // optional scalar the dry audio is multiplied with (peak normalisation), or NULL
   double snr, ref_db;
   // moving events rendered by the persistent producer/consumer launch (alr_fused.cuh); 0 for everything else
-  int fused;             // 1: H spectra live in the L2-resident ring, a_l is applied by the C-tasks
+  int small;             // 1: rendered by k_small_rir (effective RIR length <= P): no spectra in the workspace
+  int fused;             // 1 / 2: H spectra live in the L2-resident ring (k_mov_fused / k_mov_sweep), a_l applied by the consumer
   int fo0;               // ordinal of the event's first RIR among the chunk's fused RIRs (ready / consumed counters)
   long long ecap0;       // first entry of the event's (RIR, capsule) tap-energy table
 };
@@ -203,7 +204,7 @@ __global__ void k_ir_scale(const EvDev* __restrict__ evs, int n_ev, const int* _
   const int e = find_segment(ir_prefix, n_ev, w);
   const EvDev& ev = evs[e];
   const int l = w - __ldg(ir_prefix + e);
-  if (ev.fused) return;  // a_l of fused events comes from the P-tasks of k_mov_fused
+  if (ev.fused || ev.small) return;  // a_l of fused events comes from the P-tasks of k_mov_fused / k_mov_sweep, k_small_rir has its own
   double a = 1.0;
   if (ev.gain_mode == kGainDry) {
     a = stats[ev.parent].a0;  // the parent's a_0: compute_dry_audio gets the normalised IRs (synthesize.py:608)
@@ -757,6 +758,160 @@ k_ifft_ola(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ pref
     }
     // slot relative to the EVENT's range: events without IRs (k_tile) own partial slots too, so the chunk-wide CTA
     // index is not the slot index (found by tests/test_gpu_fuzz.py: every event after a no-IR event got a wrong gain)
+    partials[ev.part0 + local] = make_float2(m, s);
+  }
+}
+
+// k_small_rir: "batched small-RIR kernel" for static renders whose effective RIR fits ONE partition (taps <= P): short
+// RIRs (SOFA / anechoic HRIRs) and, above all, the dry / direct-path sub-events of compute_dry_audio, whose RIR is the
+// <= 65 ms window around the direct-path peak (synthesize.py:432-504; 1 560 taps at 24 kHz) — the general pipeline
+// spends 12 partition transforms, a spectra round trip through the workspace and four launches on them.
+// One FFT group per (event, capsule, run of kRun blocks): the RIR spectrum is computed once and STAYS IN REGISTERS; per
+// block one forward transform of the source, the pointwise product, one inverse transform, overlap-add with the tail in
+// registers, gain statistics. No spectrum ever leaves the SM. The tap window [mask_lo, mask_hi) (set by k_dry_window
+// for dry events) is shifted to tap 0 and the output written at offset mask_lo, which is the same convolution.
+// a_0 (normalize_irs) comes from the parent for dry events and is computed here otherwise (every group reduces all C
+// energies in the same fixed order, so all CTAs of an event agree bit for bit).
+__global__ void __launch_bounds__(kCtaThreads, 2)
+k_small_rir(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const float2* __restrict__ tw,
+            const float2* __restrict__ zeta, EvStat* __restrict__ stats, float2* __restrict__ partials) {
+  __shared__ FftSmem sm[kGroupsPerCta];
+  __shared__ float s_red[kGroupsPerCta][kGroup / 32];
+  __shared__ float s_max[kCtaThreads / 32], s_sum[kCtaThreads / 32];
+  const int g = threadIdx.x / kGroup, t = threadIdx.x % kGroup, bar = 1 + g;
+  const int e = find_segment(prefix, n_ev, blockIdx.x);
+  const EvDev& ev = evs[e];
+  const int local = blockIdx.x - __ldg(prefix + e);
+  const int lo = ev.mask_lo, hi = min(ev.mask_hi, ev.Lh);
+  const int wlen = max(hi - lo, 0);
+  // convolution blocks (relative to tap lo): the host sized the grid for the largest window it could be
+  const int nruns = ev.B_out;  // runs of kRun blocks (host: ceil(ceil((Lx + wmax - 1) / P) / kRun))
+  const int run = local % nruns, cg = local / nruns;
+  const int c = cg * kGroupsPerCta + g;
+  float vmax = 0.f, vsum = 0.f;
+  if (c < ev.C) {
+    const float2 zt = __ldg(zeta + t);
+    // ---- scale: a_0 * peak-normalisation scalar
+    double a0 = 1.0;
+    if (ev.gain_mode == kGainDry) {
+      a0 = stats[ev.parent].a0;
+    } else if (ev.normalize) {
+      double mean_e = 0.0;
+      for (int cc = 0; cc < ev.C; ++cc) {
+        const float* __restrict__ hc = ev.irs + (long long)cc * ev.ir_stride_c;
+        float en = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int n = t + kGroup * r;
+          const float v = (n < ev.Lh) ? __ldg(hc + n) : 0.f;
+          en = fmaf(v, v, en);
+        }
+        en = warp_sum(en);
+        if ((t & 31) == 0) s_red[g][t >> 5] = en;
+        group_sync(bar);
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < kGroup / 32; ++w) tot += s_red[g][w];
+        group_sync(bar);
+        mean_e += sqrt((double)tot) + 2.2250738585072014e-308;
+      }
+      mean_e /= ev.C;
+      a0 = mean_e > 0.0 ? 1.0 / mean_e : 0.0;
+      if (!(a0 < 3.0e38)) a0 = 0.0;
+      if (run == 0 && c == 0 && t == 0) stats[ev.stat].a0 = a0;
+    }
+    const float sc = (float)a0 * (ev.xnorm ? __ldg(ev.xnorm) : 1.f);
+    // ---- RIR spectrum (window shifted to tap 0), kept in registers in the inverse transform's input order
+    float2 H[16];
+    {
+      const float* __restrict__ src = ev.irs + (long long)c * ev.ir_stride_c + lo;
+      float a[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int n = t + kGroup * r;
+        a[r] = (n < wlen) ? __ldg(src + n) : 0.f;
+      }
+      float2 o[kM3][kR3];
+      fwd_block_to_regs(a, zt, sm[g], tw, t, bar, o);
+#pragma unroll
+      for (int m = 0; m < kM3; ++m)
+#pragma unroll
+        for (int k = 0; k < kR3; ++k) H[m + (256 / kGroup) * k] = o[m][k];  // element t + kGroup (m + 2k)
+    }
+    const float inv = 1.0f / kP;
+    const int n_conv = ev.Lx + wlen - 1;  // samples of the (shifted) convolution that carry signal
+    float* __restrict__ y = ev.y + (long long)c * ev.n_out;
+    const float* __restrict__ x = ev.x;
+    const int b0 = run * kRun, b1 = b0 + kRun;
+    // the outputs before the window offset and behind the last convolution block are exact zeros
+    if (run == 0)
+      for (int n = t; n < min(lo, ev.n_out); n += kGroup) y[n] = 0.f;
+    if (run == nruns - 1)
+      for (int n = lo + b1 * kP + t; n < ev.n_out; n += kGroup) y[n] = 0.f;
+    float tail[kM3][kR3];
+#pragma unroll
+    for (int m = 0; m < kM3; ++m)
+#pragma unroll
+      for (int k = 0; k < kR3; ++k) tail[m][k] = 0.f;
+    for (int b = max(b0 - 1, 0); b < b1; ++b) {
+      float2 o[kM3][kR3];
+      if (b * kP < ev.xlimit) {
+        float a[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int n = b * kP + t + kGroup * r;
+          a[r] = (n < ev.xlimit) ? __ldg(x + n) * sc : 0.f;
+        }
+        float2 xs[kM3][kR3];
+        fwd_block_to_regs(a, zt, sm[g], tw, t, bar, xs);
+        float2 v[16];
+#pragma unroll
+        for (int m = 0; m < kM3; ++m)
+#pragma unroll
+          for (int k = 0; k < kR3; ++k) v[m + (256 / kGroup) * k] = cmul(xs[m][k], H[m + (256 / kGroup) * k]);
+        inv_block_from_regs(v, zt, sm[g], tw, t, bar, o);
+      } else {
+#pragma unroll
+        for (int m = 0; m < kM3; ++m)
+#pragma unroll
+          for (int k = 0; k < kR3; ++k) o[m][k] = make_float2(0.f, 0.f);
+      }
+      if (b >= b0) {
+#pragma unroll
+        for (int k = 0; k < kR3; ++k)
+#pragma unroll
+          for (int m = 0; m < kM3; ++m) {
+            const int ci = b * kP + t + kGroup * m + 256 * k;  // index into the shifted convolution
+            const int n = lo + ci;
+            float a = fmaf(o[m][k].x, inv, tail[m][k]);
+            if (ci >= n_conv || n >= ev.n_valid) a = 0.f;
+            if (n < ev.n_out) {
+              y[n] = a;
+              vmax = fmaxf(vmax, fabsf(a));
+              vsum += fabsf(a);
+            }
+          }
+      }
+#pragma unroll
+      for (int m = 0; m < kM3; ++m)
+#pragma unroll
+        for (int k = 0; k < kR3; ++k) tail[m][k] = o[m][k].y * inv;
+    }
+  }
+  vmax = warp_max(vmax);
+  vsum = warp_sum(vsum);
+  if ((threadIdx.x & 31) == 0) {
+    s_max[threadIdx.x >> 5] = vmax;
+    s_sum[threadIdx.x >> 5] = vsum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f, s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCtaThreads / 32; ++w) {
+      m = fmaxf(m, s_max[w]);
+      s += s_sum[w];
+    }
     partials[ev.part0 + local] = make_float2(m, s);
   }
 }

@@ -110,6 +110,7 @@ struct alr_context {
   int fused_grid = 0;                     // resident CTAs of k_mov_fused (SMs x occupancy)
   int sm_clock_khz = 0;
   int mix_group = 0;                      // scenes per ambience-reduction + mixdown group (0: all at once)
+  int small_rir = 1;                      // k_small_rir for RIRs of at most one partition (ALR_SMALL=0: general pipeline)
   int64_t l2_persist_bytes = 0;           // L2 set aside for persisting lines (the ring of k_mov_sweep); 0: off
   int64_t l2_window_max = 0;
   HostBuf stage, stage_out, stage_aug;
@@ -164,9 +165,12 @@ struct EvSize {
   int fused = 0;       // 0 / 1 (k_mov_fused) / 2 (k_mov_sweep)
   long long h_ws = 0;  // H slots in the chunk workspace
   int n_ptask = 0, n_ctask = 0;
+  // static renders whose effective RIR fits one partition: k_small_rir, nothing in the workspace
+  bool small = false;
+  int n_small = 0, small_runs = 0;
 };
 
-int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0, int mover = 0) {
+int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0, int mover = 0, int small_mode = 0) {
   z = EvSize();
   if (u.n_channels < 1) return fail(ALR_ERR_INVALID, "event %d: n_channels must be >= 1", idx);
   if (u.n_out < 1 || !u.spatial) return fail(ALR_ERR_INVALID, "event %d: no output buffer", idx);
@@ -257,6 +261,23 @@ int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0,
   const long long n_ifft = (long long)((C + kIfftCh - 1) / kIfftCh) * ceil_div(z.B_out, kRun);
   if (z.h > 0x3ffffff0LL || n_cmac > 0x3ffffff0LL || z.xb > 0x3ffffff0LL)
     return fail(ALR_ERR_INVALID, "event %d: too large for 32-bit task indices", idx);
+  // small_mode: 0 off, 1 caller's event, 2 dry / direct-path sub-event (its RIR is the window of at most
+  // dry_low + dry_high taps that k_dry_window selects)
+  if (small_mode && !moving) {
+    const long long wmax = small_mode == 2 ? std::min<long long>(Lh, (long long)std::max(u.dry_low, 0) + std::max(u.dry_high, 0)) : Lh;
+    if (wmax >= 1 && wmax <= kP && (small_mode == 2 || C <= 8)) {
+      const int bc = ceil_div(Lx + wmax - 1, kP);
+      z.small = true;
+      z.small_runs = ceil_div(bc, kRun);
+      z.n_small = ((C + kGroupsPerCta - 1) / kGroupsPerCta) * z.small_runs;
+    }
+  }
+  if (z.small) {
+    z.h = z.xb = z.y = 0;
+    z.n_parts = z.n_small;
+    z.h_ws = 0;
+    return ALR_OK;
+  }
   z.h_ws = z.h;
   z.n_irfft = (int)z.h;
   z.n_cmac = moving ? (int)n_cmac : 0;         // generic kernel: moving events
@@ -389,7 +410,7 @@ struct Chunk {
   long long hslots = 0, xslots = 0, yslots = 0;
   int n_ir = 0, n_wband = 0, n_blk = 0;
   size_t off_evs = 0, off_irs = 0, off_wband = 0, off_lrange = 0;
-  size_t off_irfft = 0, off_ir = 0, off_xfft = 0, off_cmac = 0, off_cmacs = 0, off_ifft = 0, off_tile = 0, off_dry = 0;
+  size_t off_irfft = 0, off_ir = 0, off_xfft = 0, off_cmac = 0, off_cmacs = 0, off_ifft = 0, off_tile = 0, off_dry = 0, off_small = 0;
   size_t bytes = 0;  // blob size
   size_t base = 0;   // offset of the blob in the staging / descriptor buffers
   int part_base = 0, ir_base = 0, gain_base = 0;
@@ -419,6 +440,7 @@ void layout_chunk(Chunk& ch) {
   ch.off_ifft = take((size_t)(ne + 1) * sizeof(int));
   ch.off_tile = take((size_t)ne * sizeof(int));
   ch.off_dry = take((size_t)ne * sizeof(int));
+  ch.off_small = take((size_t)(ne + 1) * sizeof(int));
   ch.off_tasks = take((size_t)ch.n_tasks * sizeof(FusedTask));
   ch.off_pop = take((size_t)ch.n_fo * sizeof(int2));
   ch.off_ncons = take((size_t)ch.n_fo * sizeof(int2));
@@ -824,6 +846,7 @@ int alr_create(int device, alr_context** out) {
     if (const char* v = getenv("ALR_RING_MB")) ctx->ring_bytes = std::max<int64_t>(1, atoll(v)) << 20;
     if (const char* v = getenv("ALR_LOOKAHEAD")) ctx->lookahead = std::max(0, atoi(v));
     if (const char* v = getenv("ALR_MIX_GROUP")) ctx->mix_group = std::max(0, atoi(v));
+    if (const char* v = getenv("ALR_SMALL")) ctx->small_rir = atoi(v) != 0;
   }
   *out = ctx;
   return ALR_OK;
@@ -875,6 +898,8 @@ int alr_set_option(alr_context* ctx, const char* name, int64_t value) {
   } else if (n == "lookahead") {
     if (value < 0 || value > 1024) return fail(ALR_ERR_INVALID, "alr_set_option: lookahead out of range");
     ctx->lookahead = (int)value;
+  } else if (n == "small_rir") {
+    ctx->small_rir = value != 0;
   } else if (n == "mix_group") {
     if (value < 0) return fail(ALR_ERR_INVALID, "alr_set_option: mix_group must be >= 0");
     ctx->mix_group = (int)value;
@@ -1193,7 +1218,8 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     const auto& evl = *phase_events[ph];
     sizes[ph].resize(evl.size());
     for (size_t i = 0; i < evl.size(); ++i) {
-      int rc = size_event(evl[i], ph == 0 ? (int)i : dry_parent[i], sizes[ph][i], ph == 0 ? ring_slots : 0, ctx->fused);
+      int rc = size_event(evl[i], ph == 0 ? (int)i : dry_parent[i], sizes[ph][i], ph == 0 ? ring_slots : 0, ctx->fused,
+                          ctx->small_rir ? (ph == 0 ? 1 : 2) : 0);
       if (rc) return rc;
     }
     // host mode: smaller chunks give the upload / compute / download pipeline something to overlap
@@ -1628,9 +1654,10 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       int* p_ifft = (int*)(hb + ch.off_ifft);
       int* l_tile = (int*)(hb + ch.off_tile);
       int* l_dry = (int*)(hb + ch.off_dry);
+      int* p_small = (int*)(hb + ch.off_small);
       int n_tile = 0, n_dry = 0, ir_off = 0, w_off = 0, blk_off = 0, parts = ch.part_base;
       long long hs = 0, xs = 0, ys = 0, ecap_off = 0;
-      p_irfft[0] = p_ir[0] = p_xfft[0] = p_cmac[0] = p_cmacs[0] = p_ifft[0] = 0;
+      p_irfft[0] = p_ir[0] = p_xfft[0] = p_cmac[0] = p_cmacs[0] = p_ifft[0] = p_small[0] = 0;
       for (int i = 0; i < ne; ++i) {
         const int ei = ch.ev_begin + i;
         const EvSize& z = sizes[ph][ei];
@@ -1654,6 +1681,11 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         d.yslot0 = ys;
         d.part0 = parts;
         d.nparts = z.n_parts;
+        if (z.small) {
+          d.small = 1;
+          d.B_out = z.small_runs;  // k_small_rir: runs of kRun convolution blocks
+          x_used = 0;
+        }
         if (z.fused) {
           d.fused = z.fused;
           d.ecap0 = ecap_off;
@@ -1672,6 +1704,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         p_cmac[i + 1] = p_cmac[i] + z.n_cmac;
         p_cmacs[i + 1] = p_cmacs[i] + z.n_cmac_static;
         p_ifft[i + 1] = p_ifft[i] + z.n_ifft;
+        p_small[i + 1] = p_small[i] + z.n_small;
         if (!z.pass && d.N == 0) l_tile[n_tile++] = i;
       }
       int n_sweep_slots = 0;
@@ -1716,6 +1749,11 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       if (n_dry > 0) {
         k_dry_window<<<n_dry, 256, 0, st>>>(c_evs, (const int*)(db + ch.off_dry), d_stats);
         LAUNCH_CHECK(kCatOther);
+      }
+      if (p_small[ne] > 0) {
+        k_small_rir<<<p_small[ne], kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_small), ctx->d_tw, ctx->d_zeta,
+                                                        d_stats, d_parts);
+        LAUNCH_CHECK(kCatIfft);
       }
       if (n_irfft > 0) {
         k_ir_fft<<<ceil_div(n_irfft, kGroupsPerCta * kIrTasks), kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_irfft),

@@ -210,3 +210,53 @@ def test_fused_launch_with_dry_audio_and_odd_channel_counts(rnd_fused):
                                literal=False, ref_ir_channel=1, direct_path_time_ms=(6, 65))
         assert np.abs(job.spatial - res.spatial).max() <= TOL
         assert np.abs(job.dry_out - res.dry).max() <= TOL
+
+
+# ---- k_small_rir: RIRs of at most one partition ----------------------------------------------------------------------------
+@pytest.mark.parametrize("lx,lh,c", [(30000, 700, 4), (5000, 2048, 1), (100, 7, 3), (70001, 1999, 8), (2049, 2047, 2)])
+def test_small_rir_kernel_vs_oracle_and_general_pipeline(rnd, lx, lh, c):
+    """Short static RIRs take k_small_rir (spectra in registers); same result as the oracle and, to rounding, as the
+    general partitioned pipeline (small_rir = 0)."""
+    rng = np.random.default_rng(lx + lh + c)
+    x = cases.make_audio(rng, lx)
+    h = cases.make_irs(rng, c, 1, lh)
+    job = EventJob(audio=x, irs=h.astype(np.float32), n_channels=c, snr=7.0, ref_db=-60.0)
+    rnd.render([job])
+    res = orc.render_event(x, h, 7.0, -60.0, is_moving=False)
+    assert np.abs(job.spatial - res.spatial).max() <= TOL
+    general = Renderer(0, small_rir=0)
+    job2 = EventJob(audio=x, irs=h.astype(np.float32), n_channels=c, snr=7.0, ref_db=-60.0)
+    general.render([job2])
+    general.close()
+    assert np.abs(job.spatial - job2.spatial).max() <= 2e-6 * np.abs(job2.spatial).max() + 1e-9
+    assert abs(job.stats["gain"] - job2.stats["gain"]) <= 1e-5 * abs(job2.stats["gain"])
+
+
+@pytest.mark.parametrize("n_irs", [1, 9])
+def test_dry_window_through_small_rir_kernel(rnd, n_irs):
+    """compute_dry_audio (synthesize.py:432-504): the 6 ms / 65 ms window around the direct-path peak is 1 704 taps at
+    24 kHz — one partition — whatever the RIR length; static and moving parents, raw length Lx + Lh - 1."""
+    rng = np.random.default_rng(90 + n_irs)
+    x = cases.make_audio(rng, 40000)
+    h = cases.make_irs(rng, 4, n_irs, 24000)
+    job = EventJob(audio=x, irs=h.astype(np.float32), n_channels=4, snr=12.0, ref_db=-65.0, dry=(2, 144, 1560))
+    if n_irs > 1:
+        job.ir_frames, job.n_frames = moving_frames(40000 / 24000.0, 24000.0, n_irs, 40000)
+    rnd.render([job])
+    res = orc.render_event(x, h, 12.0, -65.0, is_moving=n_irs > 1, duration=40000 / 24000.0, sample_rate=24000.0,
+                           literal=False, ref_ir_channel=2, direct_path_time_ms=(6, 65))
+    assert job.dry_out.shape == (40000 + 24000 - 1,)
+    assert np.abs(job.dry_out - res.dry).max() <= TOL
+    assert np.abs(job.spatial - res.spatial).max() <= TOL
+    general = Renderer(0, small_rir=0)
+    job2 = EventJob(audio=x, irs=h.astype(np.float32), n_channels=4, snr=12.0, ref_db=-65.0, dry=(2, 144, 1560))
+    if n_irs > 1:
+        job2.ir_frames, job2.n_frames = moving_frames(40000 / 24000.0, 24000.0, n_irs, 40000)
+    general.render([job2])
+    general.close()
+    assert job.stats["dry_peak"] == job2.stats["dry_peak"]
+    assert np.abs(job.dry_out - job2.dry_out).max() <= 2e-6 * np.abs(job2.dry_out).max() + 1e-9
+    outside = np.ones(job.dry_out.shape[0], bool)
+    pk = job.stats["dry_peak"]
+    outside[max(pk - 144, 0):pk + 1560 + 40000] = False
+    assert np.all(job.dry_out[outside] == 0.0)  # exact zeros where no windowed tap can reach
