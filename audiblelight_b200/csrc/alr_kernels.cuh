@@ -1201,7 +1201,7 @@ struct AugDev {       // one (event, op) application
   int fin_shape, fout_shape, fin, fout;
   int chunk0;         // first entry of the chunk-state scratch (IIR ops)
   int nchunks;
-  float p[6];
+  double p[6];        // coefficients in double: rounding a pole near the unit circle to float32 alone costs ~1e-5 of output
 };
 
 __device__ __forceinline__ float fade_in_curve(int shape, float f) {
@@ -1239,7 +1239,7 @@ __global__ void k_aug_pointwise(const AugDev* __restrict__ ops) {
     // outputs (1 - mix) x[n] + mix d[n]. The D residue classes n = r (mod D) are independent first-order recurrences
     // d[n] = x[n-D] + feedback d[n-D]: one thread per residue, coalesced across r.
     const int D = (int)o.p[0];
-    const float fb = o.p[1], wet = o.p[2], dry = 1.f - o.p[2];
+    const float fb = (float)o.p[1], wet = (float)o.p[2], dry = 1.f - (float)o.p[2];
     if (D <= 0) {
       for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < L; n += gridDim.x * blockDim.x) o.dst[n] = o.src[n];
       return;
@@ -1259,7 +1259,7 @@ __global__ void k_aug_pointwise(const AugDev* __restrict__ ops) {
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < L; n += gridDim.x * blockDim.x) {
     float v;
     switch (o.type) {
-      case kAugGain: v = o.p[0] * o.src[n]; break;
+      case kAugGain: v = (float)o.p[0] * o.src[n]; break;
       case kAugInvert: v = -o.src[n]; break;
       case kAugReverse: v = o.src[L - 1 - n]; break;
       case kAugFade: {
@@ -1275,7 +1275,7 @@ __global__ void k_aug_pointwise(const AugDev* __restrict__ ops) {
       }
       case kAugPreemph: {
         // librosa.effects.preemphasis: lfilter([1, -coef], [1], x, zi = 2 x[0] - x[1])  ->  y[0] = x[0] + zi
-        const float c = o.p[0];
+        const float c = (float)o.p[0];
         if (n == 0) v = o.src[0] + (L > 1 ? 2.f * o.src[0] - o.src[1] : o.src[0]);
         else v = o.src[n] - c * o.src[n - 1];
         break;
@@ -1290,9 +1290,9 @@ __global__ void k_aug_pointwise(const AugDev* __restrict__ ops) {
 //   y = b0 x + s1;  s1' = b1 x - a1 y + s2;  s2' = b2 x - a2 y
 // a chunk maps s_in -> A^Lc s_in + s_zs (A = [[-a1, 1], [-a2, 0]]). Pass 1: zero-state run of every chunk (s_zs);
 // combine: sequential over the chunks of one op in double; pass 2: re-run every chunk from its true s_in.
-__device__ __forceinline__ void iir_coeffs(const AugDev& o, float& b0, float& b1, float& b2, float& a1, float& a2) {
+__device__ __forceinline__ void iir_coeffs(const AugDev& o, double& b0, double& b1, double& b2, double& a1, double& a2) {
   if (o.type == kAugDeemph) {  // y[n] = x[n] + coef y[n-1]
-    b0 = 1.f; b1 = 0.f; b2 = 0.f; a1 = -o.p[0]; a2 = 0.f;
+    b0 = 1.0; b1 = 0.0; b2 = 0.0; a1 = -o.p[0]; a2 = 0.0;
   } else {
     b0 = o.p[0]; b1 = o.p[1]; b2 = o.p[2]; a1 = o.p[3]; a2 = o.p[4];
   }
@@ -1304,12 +1304,15 @@ __device__ __forceinline__ void iir_coeffs(const AugDev& o, float& b0, float& b1
 // sample by sample at a 2 KB lane stride; 1.2 ms with a transposing tile but 4 loads in flight; 0.54 ms with
 // per-thread 16-byte loads (each warp request still touched 32 lines: L1TEX wavefront bound); this version is bound
 // by the recurrence itself.
+// The state (s1, s2), the coefficients and the chunk hand-over run in float64: a float32 recurrence loses ~eps / (1 - |pole|)
+// of the signal (2e-5 of full scale for a 32 Hz high-pass at 24 kHz), more than the 1e-5 the whole path is allowed. Samples
+// stay float32 in memory (what Event.load_audio returns), each output is rounded once.
 constexpr int kIirCta = 128, kIirSub = 32;
 
 template <bool WRITE>
 __global__ void __launch_bounds__(kIirCta)
 k_iir_pass(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix, int n_ops, int n_chunks,
-           float2* __restrict__ zs) {
+           double2* __restrict__ zs) {
   __shared__ float tile[kIirCta / 32][32][33];
   __shared__ const float* s_src[kIirCta];
   __shared__ float* s_dst[kIirCta];
@@ -1317,11 +1320,11 @@ k_iir_pass(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row0 = warp * 32;
   const int c = blockIdx.x * kIirCta + threadIdx.x;
   const bool live = c < n_chunks;
-  float b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f;
+  double b0 = 0.0, b1 = 0.0, b2 = 0.0, a1 = 0.0, a2 = 0.0;
   int n0 = 0, n1 = 0;
   const float* src = nullptr;
   float* dst = nullptr;
-  float s1 = 0.f, s2 = 0.f, corr = 0.f, cpow = 1.f, coef = 0.f;
+  double s1 = 0.0, s2 = 0.0, corr = 0.0, cpow = 1.0, coef = 0.0;
   bool deemph = false;
   if (live) {
     const int oi = find_segment(chunk_prefix, n_ops, c);
@@ -1338,8 +1341,8 @@ k_iir_pass(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix,
       if (o.type == kAugDeemph && o.L > 1) {
         deemph = true;
         coef = o.p[0];
-        corr = ((2.f - coef) * src[0] - src[1]) / (3.f - coef);
-        cpow = powf(coef, (float)n0);
+        corr = ((2.0 - coef) * (double)src[0] - (double)src[1]) / (3.0 - coef);
+        cpow = pow(coef, (double)n0);
       }
     }
   }
@@ -1365,16 +1368,16 @@ k_iir_pass(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix,
 #pragma unroll
     for (int j = 0; j < kIirSub; ++j) {
       if (j < cnt) {
-        const float x = T[lane][j];
-        const float y = fmaf(b0, x, s1);
-        s1 = fmaf(b1, x, fmaf(-a1, y, s2));
-        s2 = fmaf(b2, x, -a2 * y);
+        const double x = (double)T[lane][j];
+        const double y = fma(b0, x, s1);
+        s1 = fma(b1, x, fma(-a1, y, s2));
+        s2 = fma(b2, x, -a2 * y);
         if (WRITE) {
           if (deemph) {
-            T[lane][j] = y - corr * cpow;
+            T[lane][j] = (float)(y - corr * cpow);
             cpow *= coef;
           } else {
-            T[lane][j] = y;
+            T[lane][j] = (float)y;
           }
         }
       }
@@ -1389,17 +1392,17 @@ k_iir_pass(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix,
       __syncwarp();
     }
   }
-  if (!WRITE && live) zs[c] = make_float2(s1, s2);
+  if (!WRITE && live) zs[c] = make_double2(s1, s2);
 }
 
 // One WARP per op: lanes fetch 32 zero-state results at once (one coalesced request instead of 32 dependent
 // round trips), the carry is then chained through the batch from registers with shuffles. blockDim = 128.
 __global__ void k_iir_combine(const AugDev* __restrict__ ops, const int* __restrict__ chunk_prefix, int n_ops,
-                              float2* __restrict__ zs) {
+                              double2* __restrict__ zs) {
   const int oi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (oi >= n_ops) return;
   const AugDev& o = ops[oi];
-  float b0, b1, b2, a1f, a2f;
+  double b0, b1, b2, a1f, a2f;
   iir_coeffs(o, b0, b1, b2, a1f, a2f);
   // M = A^kIirChunk by repeated squaring (kIirChunk is a power of two)
   double m00 = -a1f, m01 = 1.0, m10 = -a2f, m11 = 0.0;
@@ -1412,20 +1415,20 @@ __global__ void k_iir_combine(const AugDev* __restrict__ ops, const int* __restr
   const int c0 = chunk_prefix[oi], c1 = chunk_prefix[oi + 1];
   for (int cb = c0; cb < c1; cb += 32) {
     const int c = cb + lane;
-    const float2 z = c < c1 ? zs[c] : make_float2(0.f, 0.f);
-    float in1 = 0.f, in2 = 0.f;
+    const double2 z = c < c1 ? zs[c] : make_double2(0.0, 0.0);
+    double in1 = 0.0, in2 = 0.0;
 #pragma unroll 8
     for (int j = 0; j < 32; ++j) {
-      const float zx = __shfl_sync(0xffffffffu, z.x, j), zy = __shfl_sync(0xffffffffu, z.y, j);
+      const double zx = __shfl_sync(0xffffffffu, z.x, j), zy = __shfl_sync(0xffffffffu, z.y, j);
       if (lane == j) {  // the true entry state of chunk cb + j replaces its zero-state result
-        in1 = (float)s1;
-        in2 = (float)s2;
+        in1 = s1;
+        in2 = s2;
       }
       const double t1 = m00 * s1 + m01 * s2 + zx, t2 = m10 * s1 + m11 * s2 + zy;
       s1 = t1;
       s2 = t2;
     }
-    if (c < c1) zs[c] = make_float2(in1, in2);
+    if (c < c1) zs[c] = make_double2(in1, in2);
   }
 }
 

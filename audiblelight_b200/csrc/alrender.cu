@@ -265,7 +265,7 @@ int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0,
   // dry_low + dry_high taps that k_dry_window selects)
   if (small_mode && !moving) {
     const long long wmax = small_mode == 2 ? std::min<long long>(Lh, (long long)std::max(u.dry_low, 0) + std::max(u.dry_high, 0)) : Lh;
-    if (wmax >= 1 && wmax <= kP && (small_mode == 2 || C <= 8)) {
+    if (wmax >= 1 && wmax <= kP && (small_mode == 2 || C <= 2)) {  // short RIRs with more capsules: the source transform would be repeated per capsule (tie at C = 4, profiles/r02_small_rir.txt)
       const int bc = ceil_div(Lx + wmax - 1, kP);
       z.small = true;
       z.small_runs = ceil_div(bc, kRun);
@@ -1130,7 +1130,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
           a.L = L;
           if (uin.n_aug_ops <= 0) {
             a.type = kAugGain;
-            a.p[0] = 1.f;
+            a.p[0] = 1.0;
           } else {
             const alr_aug_op& op = uin.aug_ops[l];
             if (op.type < 0 || op.type > kAugDelay) return fail(ALR_ERR_INVALID, "event %d: bad augmentation type %d", (int)i, op.type);
@@ -1139,7 +1139,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
             a.fout_shape = op.fade_out_shape;
             a.fin = std::min(std::max(op.fade_in_samples, 0), L);
             a.fout = std::min(std::max(op.fade_out_samples, 0), L);
-            for (int q = 0; q < 6; ++q) a.p[q] = (float)op.p[q];
+            for (int q = 0; q < 6; ++q) a.p[q] = op.p[q];
           }
           if (a.type == kAugBiquad || a.type == kAugDeemph) {
             a.nchunks = ceil_div(L, kIirChunk);
@@ -1176,7 +1176,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     size_t n_ops_total = 0;
     for (int l = 0; l < kAugLevels; ++l) n_ops_total += aug_point[l].size() + aug_iir[l].size();
     aug_desc_reserved = xnorm_bytes + n_ops_total * (sizeof(AugDev) + sizeof(int)) + kAugLevels * 3 * 64 +
-                        aug_norm.size() * sizeof(NormDev) + (size_t)std::max(aug_chunks_total, 1) * sizeof(float2) +
+                        aug_norm.size() * sizeof(NormDev) + (size_t)std::max(aug_chunks_total, 1) * sizeof(double2) +
                         std::max<size_t>(aug_norm.size(), 1) * kAugSlices * sizeof(float) + 4096;
     int rc = ctx->augdesc.ensure(aug_desc_reserved);
     if (rc) return rc;
@@ -1582,7 +1582,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     }
     const size_t off_norm = ab.add(aug_norm.data(), aug_norm.size() * sizeof(NormDev));
     const size_t off_zs = align_up(ab.bytes.size(), 256);
-    const size_t off_peaks = align_up(off_zs + (size_t)std::max(aug_chunks_total, 1) * sizeof(float2), 256);
+    const size_t off_peaks = align_up(off_zs + (size_t)std::max(aug_chunks_total, 1) * sizeof(double2), 256);
     const size_t aug_total = off_peaks + std::max<size_t>(aug_norm.size(), 1) * kAugSlices * sizeof(float);
     if (aug_total > aug_desc_reserved) return fail(ALR_ERR_INVALID, "internal: augmentation descriptor bound exceeded");
     {
@@ -1597,7 +1597,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       int rc = compute_waits_for_uploads();
       if (rc) return rc;
     }
-    float2* d_zs = (float2*)(ad + off_zs);
+    double2* d_zs = (double2*)(ad + off_zs);
     float* d_peaks = (float*)(ad + off_peaks);
     for (int l = 0; l < kAugLevels; ++l) {
       if (!aug_point[l].empty()) {

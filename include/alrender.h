@@ -198,7 +198,7 @@ int alr_set_workspace_limit(alr_context* ctx, int64_t bytes);
  *                 input-driven sweeper warps with shared-memory accumulators), spectra stay in an L2-resident ring
  *   "ring_bytes"  size of that ring (default 64 MiB)
  *   "lookahead"   runs of output blocks whose RIR spectra are produced ahead of their consumers (default 2)
- *   "small_rir"   1 (default): static renders whose effective RIR fits one partition (short RIRs with at most 8 capsules, and
+ *   "small_rir"   1 (default): static renders whose effective RIR fits one partition (short RIRs with at most 2 capsules, and
  *                 the dry / direct-path sub-events of compute_dry_audio) go through k_small_rir, which keeps every spectrum
  *                 in registers; 0: the general partitioned pipeline
  *   "mix_group"   scenes per ambience-reduction + mixdown launch group, sized so that a group's ambience stays in L2
