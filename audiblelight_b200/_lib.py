@@ -34,7 +34,8 @@ class AlrAugOp(C.Structure):
 class AlrScene(C.Structure):
     _fields_ = [
         ("n_channels", C.c_int32), ("n_ambience", C.c_int32), ("n_samples", C.c_int64),
-        ("ambience", C.c_void_p), ("ambience_ref_db", C.c_void_p), ("mix", C.c_void_p), ("pcm16", C.c_void_p),
+        ("ambience", C.c_void_p), ("ambience_ref_db", C.c_void_p), ("mix", C.c_void_p), ("ambience_seed", C.c_void_p),
+        ("pcm16", C.c_void_p),
     ]
 
 

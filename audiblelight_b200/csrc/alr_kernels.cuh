@@ -1503,6 +1503,93 @@ __global__ void k_pcm16(const SceneDev* __restrict__ scenes) {
   for (int c = 0; c < C; ++c) out[c] = (short)__float2int_rn(s.mix[(long long)c * s.T + t] * 32767.f);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// f3: Gaussian ambience generated on the device (Ambience.load_ambience with noise="gaussian", ambience.py:155-163 +
+// per-channel peak normalisation :210-214). The reference draws it from numpy's UNSEEDED global generator, so there is
+// no sample-level parity to keep: what is kept is the distribution (i.i.d. N(0, 1) per sample, channels independent)
+// and the normalisation. Counter-based Philox4x32-10 keyed by (seed, layer), Box-Muller; the stream of a layer depends
+// only on its seed, channel and sample index, never on the launch geometry. Two passes that both REGENERATE the
+// numbers: the first only reduces max|x| per channel (no memory traffic), the second writes x / (max + tiny).
+struct GenDev {
+  float* out;            // (C, T)
+  long long T;
+  int C;
+  int part0;             // first per-channel peak slot
+  unsigned long long seed;
+};
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                                              unsigned (&r)[4]) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
+}
+// four N(0, 1) samples for (seed, channel c, samples 4 q .. 4 q + 3)
+__device__ __forceinline__ void gauss4(unsigned long long seed, int c, unsigned long long q, float (&g)[4]) {
+  unsigned r[4];
+  philox4x32_10((unsigned)q, (unsigned)(q >> 32), (unsigned)c, 0x414c5221u, (unsigned)seed, (unsigned)(seed >> 32), r);
+  // Box-Muller on uniforms in (0, 1]
+  const float u0 = ((float)(r[0] >> 8) + 1.0f) * (1.0f / 16777216.0f), u1 = (float)(r[1] >> 8) * (1.0f / 16777216.0f);
+  const float u2 = ((float)(r[2] >> 8) + 1.0f) * (1.0f / 16777216.0f), u3 = (float)(r[3] >> 8) * (1.0f / 16777216.0f);
+  const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+  float sa, ca, sb, cb;
+  sincospif(2.0f * u1, &sa, &ca);
+  sincospif(2.0f * u3, &sb, &cb);
+  g[0] = ra * ca; g[1] = ra * sa; g[2] = rb * cb; g[3] = rb * sb;
+}
+constexpr int kGenSlices = 32;
+// grid = (kGenSlices, C, layers). WRITE = false: per-slice max|x| -> peaks[(part0 + c) * kGenSlices + slice]
+template <bool WRITE>
+__global__ void __launch_bounds__(256)
+k_amb_gauss(const GenDev* __restrict__ gens, float* __restrict__ peaks) {
+  __shared__ float s_max[8];
+  const GenDev& gd = gens[blockIdx.z];
+  const int c = blockIdx.y;
+  if (c >= gd.C) return;
+  const unsigned long long nq = (unsigned long long)((gd.T + 3) >> 2);
+  float inv = 1.f;
+  if (WRITE) {
+    float m = 0.f;
+    for (int i = 0; i < kGenSlices; ++i) m = fmaxf(m, peaks[(gd.part0 + c) * kGenSlices + i]);
+    inv = 1.0f / (m + 1.17549435e-38f);  // channel / max(|channel| + tiny(float32 result))
+  }
+  float vmax = 0.f;
+  float* __restrict__ out = gd.out + (long long)c * gd.T;
+  for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq;
+       q += (unsigned long long)gridDim.x * blockDim.x) {
+    float g[4];
+    gauss4(gd.seed, c, q, g);
+    const long long n = (long long)(q << 2);
+    if (WRITE) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (n + i < gd.T) out[n + i] = g[i] * inv;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (n + i < gd.T) vmax = fmaxf(vmax, fabsf(g[i]));
+    }
+  }
+  if (!WRITE) {
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = vmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = 0.f;
+      for (int w = 0; w < 8; ++w) m = fmaxf(m, s_max[w]);
+      peaks[(gd.part0 + c) * kGenSlices + blockIdx.x] = m;
+    }
+  }
+}
+
 // ---- unit-test kernels for the FFT core ---------------------------------------------------------------------
 __global__ void __launch_bounds__(kCtaThreads)
 k_debug_rfft(const float* __restrict__ in, long long n_blocks, long long in_stride, int n_valid,

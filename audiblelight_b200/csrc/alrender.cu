@@ -100,7 +100,7 @@ struct alr_context {
   float2* d_tw = nullptr;    // exp(-2 pi i m / P), m < P
   float2* d_zeta = nullptr;  // exp(+i pi t / 2P), t < 64 (twist seed of thread t)
   float* d_win = nullptr;  // sin^2(pi p / 256), p < 128
-  DevBuf spec, desc, misc, arena, augbuf, augdesc, ring;
+  DevBuf spec, desc, misc, arena, augbuf, augdesc, ring, ambgen;
   // persistent producer/consumer launch for moving events (alr_fused.cuh)
   int fused = 0;                          // moving events: 0 = k_ir_fft + k_cmac, 1 = k_mov_fused (alr_fused.cuh, experiment,
                                           // profiles/r02_fused_ring.txt), 2 = k_mov_sweep (alr_sweep.cuh)
@@ -866,6 +866,7 @@ void alr_destroy(alr_context* ctx) {
   ctx->augbuf.release();
   ctx->augdesc.release();
   ctx->ring.release();
+  ctx->ambgen.release();
   ctx->stage.release();
   ctx->stage_out.release();
   ctx->stage_aug.release();
@@ -939,10 +940,49 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
   std::vector<alr_event> events(events_in, events_in + n_events);
   std::vector<alr_scene> scenes(scenes_in, scenes_in + n_scenes);
   std::vector<std::vector<const float*>> amb_ptrs(n_scenes);
+  // f3: ambience layers without a buffer are Gaussian noise generated on the device (alr_scene.ambience_seed)
+  struct GenLayer {
+    int scene, layer;
+    size_t off;
+  };
+  std::vector<GenLayer> gen_layers;
+  std::vector<std::vector<char>> amb_gen(n_scenes);
+  size_t gen_bytes = 0;
+  int gen_channels = 0;
   for (int64_t s = 0; s < n_scenes; ++s) {
     if (scenes[s].n_ambience > 0 && scenes[s].ambience) {
       amb_ptrs[s].assign(scenes[s].ambience, scenes[s].ambience + scenes[s].n_ambience);
+      amb_gen[s].assign(scenes[s].n_ambience, 0);
+      for (int a = 0; a < scenes[s].n_ambience; ++a) {
+        if (amb_ptrs[s][a]) continue;
+        if (!scenes[s].ambience_seed) return fail(ALR_ERR_INVALID, "scene %d: null ambience %d (and no ambience_seed)", (int)s, a);
+        if (scenes[s].n_channels < 1 || scenes[s].n_samples < 1) return fail(ALR_ERR_INVALID, "scene %d: bad shape", (int)s);
+        amb_gen[s][a] = 1;
+        gen_layers.push_back({(int)s, a, gen_bytes});
+        gen_bytes += align_up((size_t)scenes[s].n_channels * scenes[s].n_samples * sizeof(float), 256);
+        gen_channels += scenes[s].n_channels;
+      }
       scenes[s].ambience = amb_ptrs[s].data();
+    }
+  }
+  std::vector<GenDev> h_gens;
+  size_t gen_off_peaks = 0, gen_off_data = 0;
+  if (!gen_layers.empty()) {
+    gen_off_peaks = align_up(gen_layers.size() * sizeof(GenDev), 256);
+    gen_off_data = align_up(gen_off_peaks + (size_t)gen_channels * kGenSlices * sizeof(float), 256);
+    int rc = ctx->ambgen.ensure(gen_off_data + gen_bytes);
+    if (rc) return rc;
+    int part = 0;
+    for (const GenLayer& gl : gen_layers) {
+      GenDev gd;
+      gd.out = (float*)((char*)ctx->ambgen.p + gen_off_data + gl.off);
+      gd.T = scenes[gl.scene].n_samples;
+      gd.C = scenes[gl.scene].n_channels;
+      gd.part0 = part;
+      gd.seed = scenes[gl.scene].ambience_seed[gl.layer];
+      part += gd.C;
+      h_gens.push_back(gd);
+      amb_ptrs[gl.scene][gl.layer] = gd.out;  // a DEVICE pointer from here on, also in host mode
     }
   }
 
@@ -1026,6 +1066,10 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       size_t bytes = (size_t)u.n_channels * u.n_samples * sizeof(float);
       for (int a = 0; a < u.n_ambience; ++a) {
         const float* p = amb_ptrs[s][a];
+        if (amb_gen[s][a]) {  // generated on the device: nothing to upload
+          off_amb[s].push_back(0);
+          continue;
+        }
         if (!p) return fail(ALR_ERR_INVALID, "scene %d: null ambience", (int)s);
         auto it = seen.find(p);
         size_t off;
@@ -1071,7 +1115,8 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
     }
     for (int64_t s = 0; s < n_scenes; ++s) {
       alr_scene& u = scenes[s];
-      for (int a = 0; a < u.n_ambience; ++a) amb_ptrs[s][a] = (const float*)(base + off_amb[s][a]);
+      for (int a = 0; a < u.n_ambience; ++a)
+        if (!amb_gen[s][a]) amb_ptrs[s][a] = (const float*)(base + off_amb[s][a]);
       out_mix.push_back({u.mix, base + off_mix[s], (size_t)u.n_channels * u.n_samples * sizeof(float)});
       u.mix = (float*)(base + off_mix[s]);
       if (u.pcm16) {
@@ -1376,6 +1421,21 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
   float* d_ecap = (float*)(mbase + mo_ecap);
   CUDA_TRY(cudaMemsetAsync(d_stats, 0, std::max<size_t>(n_events, 1) * sizeof(EvStat), st));
   CUDA_TRY(cudaMemsetAsync(d_ctl, 0, sizeof(FusedCtl), st));
+  if (!h_gens.empty()) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->ambgen.p, h_gens.data(), h_gens.size() * sizeof(GenDev), cudaMemcpyHostToDevice, st));
+    int max_c = 0;
+    for (const GenDev& gd : h_gens) max_c = std::max(max_c, gd.C);
+    float* d_peaks = (float*)((char*)ctx->ambgen.p + gen_off_peaks);
+    for (size_t g0 = 0; g0 < h_gens.size(); g0 += 32768) {
+      const unsigned cnt = (unsigned)std::min<size_t>(32768, h_gens.size() - g0);
+      const dim3 grid(kGenSlices, (unsigned)max_c, cnt);
+      k_amb_gauss<false><<<grid, 256, 0, st>>>((const GenDev*)ctx->ambgen.p + g0, d_peaks);
+      CUDA_TRY(cudaGetLastError());
+      k_amb_gauss<true><<<grid, 256, 0, st>>>((const GenDev*)ctx->ambgen.p + g0, d_peaks);
+      CUDA_TRY(cudaGetLastError());
+      ctx->prof.kernel_launches += 2;
+    }
+  }
   ctx->prof.workspace_bytes = (int64_t)(ctx->spec.cap + ctx->misc.cap + ctx->desc.cap + ctx->arena.cap);
   ctx->prof.n_chunks = (int64_t)(chunks[0].size() + chunks[1].size());
   {

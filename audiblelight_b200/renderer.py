@@ -81,8 +81,9 @@ class SceneJob:
     """One (scene, microphone) mixdown; mirrors `alr_scene`."""
     n_channels: int
     n_samples: int
-    ambience: Sequence[object] = ()       # each (C, T) float32
+    ambience: Sequence[object] = ()       # each (C, T) float32, or None: Gaussian noise generated on the device (f3)
     ambience_ref_db: Sequence[float] = ()
+    ambience_seed: Sequence[int] = ()     # one per layer when any layer is None (Philox key of the generated noise)
     mix: object = None                    # (C, T) float32 out
     pcm16: object = None                  # optional (T, C) int16 out: the PCM_16 samples sf.write(path, mix.T, sr) stores
     keep_mix: bool = True                 # False (host arrays, pcm16 given): only the PCM copy is downloaded
@@ -323,7 +324,11 @@ class Renderer:
             n_amb = len(s.ambience)
             b.n_ambience = n_amb
             if n_amb:
+                if any(amb is None for amb in s.ambience) and len(s.ambience_seed) != n_amb:
+                    raise ValueError("ambience_seed needs one entry per ambience layer when a layer is generated (None)")
                 for amb in s.ambience:
+                    if amb is None:
+                        continue
                     if tuple(amb.shape) != (s.n_channels, s.n_samples):
                         raise ValueError(
                             f"Scene ambient noise does not match expected shape. "
@@ -336,6 +341,10 @@ class Renderer:
                 keep += [ptrs, dbs]
                 b.ambience = C.cast(ptrs, C.c_void_p)
                 b.ambience_ref_db = C.cast(dbs, C.c_void_p)
+                if len(s.ambience_seed) == n_amb:
+                    seeds = (C.c_uint64 * n_amb)(*[int(v) & 0xFFFFFFFFFFFFFFFF for v in s.ambience_seed])
+                    keep.append(seeds)
+                    b.ambience_seed = C.cast(seeds, C.c_void_p)
             if s.pcm16 is not None:
                 if tuple(s.pcm16.shape) != (s.n_samples, s.n_channels) or "int16" not in str(s.pcm16.dtype):
                     raise ValueError("pcm16 must be an int16 array of shape (n_samples, n_channels)")
@@ -348,7 +357,9 @@ class Renderer:
                 b.mix = 0
                 continue
             if s.mix is None:
-                ref = s.ambience[0] if n_amb else next((e.spatial for e in events if e.spatial is not None), None)
+                ref = next((a for a in s.ambience if a is not None), None)
+                if ref is None:
+                    ref = next((e.spatial for e in events if e.spatial is not None), None)
                 if ref is None:
                     ref = np.empty(0, dtype=np.float32)
                 s.mix = self._alloc_like(ref, (s.n_channels, s.n_samples))

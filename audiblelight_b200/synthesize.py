@@ -48,6 +48,12 @@ _lock = threading.Lock()
 # arithmetic follows the published formulas but is not pinned against the real dependencies (see augment.py).
 DEVICE_AUGMENTATIONS = False
 
+# f3 (opt-in): Gaussian ambience (Ambience(noise="gaussian"), ambience.py:155-163) that has not been loaded yet is drawn on
+# the device inside the mixdown call instead of on the host and uploaded (23 MB per one-minute 4-channel layer). The
+# reference draws it from numpy's unseeded global generator, so only the distribution is defined; the device stream is
+# keyed by a seed taken from that same global generator. `ambience.audio` stays unset (nothing comes back to the host).
+DEVICE_AMBIENCE = False
+
 
 def _load_raw_audio(event) -> np.ndarray:
     """The first half of Event.load_audio (event.py:519-527): the resampled mono clip BEFORE augmentation and
@@ -342,11 +348,18 @@ def _mix_jobs_for_mic(scene, mic_alias: str, scene_index: int, prerendered: bool
     channels = max(ev.spatial_audio[mic_alias].shape[0] for ev in scene.events.values()) if prerendered else \
         max(j.n_channels for j in event_jobs)
     total = scene_samples(scene.duration, scene.sample_rate)
-    ambs, dbs = [], []
+    ambs, dbs, seeds = [], [], []
     if len(scene.ambience) > 0:
         for ambience in scene.ambience.values():
             if not _is_ambience(ambience):
                 raise TypeError(f"Expected scene ambient noise to be of type Ambience, but got {type(ambience)}!")
+            if (DEVICE_AMBIENCE and getattr(ambience, "beta", None) == "gaussian"
+                    and getattr(ambience, "audio", None) is None and int(getattr(ambience, "channels", channels)) == channels):
+                ambs.append(None)
+                dbs.append(float(ambience.ref_db))
+                seeds.append(int(np.random.randint(0, 2 ** 62)))
+                continue
+            seeds.append(0)
             noise = ambience.load_ambience(normalize=True)
             if noise.shape != (channels, total):
                 raise ValueError(
@@ -355,7 +368,8 @@ def _mix_jobs_for_mic(scene, mic_alias: str, scene_index: int, prerendered: bool
                 )
             ambs.append(_as_f32(noise, pool))
             dbs.append(float(ambience.ref_db))
-    sjob = SceneJob(n_channels=channels, n_samples=total, ambience=ambs, ambience_ref_db=dbs)
+    sjob = SceneJob(n_channels=channels, n_samples=total, ambience=ambs, ambience_ref_db=dbs,
+                    ambience_seed=seeds if any(a is None for a in ambs) else ())
     placements = []
     for event in scene.events.values():
         s0, s1 = event_slice(event.scene_start, event.scene_end, scene.sample_rate, total)
@@ -545,13 +559,15 @@ _PATCHED = ("render_event_audio", "render_audio_for_all_scene_events", "generate
 _originals = {}
 
 
-def install(device_augmentations: bool = False) -> None:
+def install(device_augmentations: bool = False, device_ambience: bool = False) -> None:
     """Rebinds the hot-path functions on `audiblelight.synthesize`. `Scene.generate` imports them at call time
     (core.py:1828-1831), so every existing caller (tests, scripts/seld/generate_dataset.py) picks them up.
-    `device_augmentations=True` additionally moves linear `Event.augmentations` chains onto the GPU (f1)."""
+    `device_augmentations=True` additionally moves linear `Event.augmentations` chains onto the GPU (f1),
+    `device_ambience=True` draws not-yet-loaded Gaussian ambience on the GPU (f3, see DEVICE_AMBIENCE)."""
     import audiblelight.synthesize as ref  # noqa
-    global DEVICE_AUGMENTATIONS
+    global DEVICE_AUGMENTATIONS, DEVICE_AMBIENCE
     DEVICE_AUGMENTATIONS = bool(device_augmentations)
+    DEVICE_AMBIENCE = bool(device_ambience)
     g = globals()
     for name in _PATCHED:
         if name not in _originals:

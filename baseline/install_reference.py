@@ -45,6 +45,13 @@ def install(src_root: str = SRC_DEFAULT) -> bool:
             s, d = os.path.join(dirpath, fn), os.path.join(DEST, rel, fn)
             shutil.copyfile(s, d)
             lines.append(f"{_sha(s)}  {os.path.join(rel, fn)}")
+    # worldstate.py:37 reads <project root>/resources/mp3d_material_config.json at import time
+    for rel in ("resources/mp3d_material_config.json",):
+        sfile = os.path.join(src_root, rel)
+        if os.path.exists(sfile):
+            os.makedirs(os.path.dirname(os.path.join(DEST, rel)), exist_ok=True)
+            shutil.copyfile(sfile, os.path.join(DEST, rel))
+            lines.append(f"{_sha(sfile)}  {rel}")
     with open(os.path.join(DEST, "MANIFEST.sha256"), "w") as f:
         f.write("\n".join(sorted(lines)) + "\n")
     return True

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ALR_VERSION 100
+#define ALR_VERSION 200
 
 enum {
   ALR_OK = 0,
@@ -140,10 +140,16 @@ typedef struct alr_scene {
   int32_t n_channels;            /* C */
   int32_t n_ambience;            /* number of ambience layers (scene.ambience, :335-356) */
   int64_t n_samples;             /* T = round(scene.duration * sr) (:331) */
-  const float* const* ambience;  /* HOST array of n_ambience pointers, each (C, T) float32 == Ambience.load_ambience() */
+  const float* const* ambience;  /* HOST array of n_ambience pointers, each (C, T) float32 == Ambience.load_ambience().
+                                    An entry may be NULL when ambience_seed is given: that layer is GENERATED on the device */
   const double* ambience_ref_db; /* HOST array (n_ambience) */
   float* mix;                    /* out (C, T) float32 -> scene.audio[mic]. With ALR_MEM_HOST it may be NULL when pcm16
                                     is given (only the PCM copy is downloaded) */
+  const uint64_t* ambience_seed; /* optional HOST array (n_ambience), NULL = every layer is an input. For a layer whose
+                                    ambience[k] is NULL: Gaussian noise, Ambience(noise="gaussian").load_ambience()
+                                    (ambience.py:155-163, peak-normalised per channel :210-214), drawn on the device
+                                    from Philox4x32-10 keyed with ambience_seed[k] ("next" row f3). The reference uses
+                                    numpy's unseeded global generator there, so only the distribution is defined. */
   int16_t* pcm16;                /* optional out (T, C) interleaved 16-bit PCM: the sample data Scene.generate stores with
                                     sf.write(path, mix.T, sr) (core.py:1840-1847; libsndfile's default WAV subtype PCM_16,
                                     float -> short as lrintf(x * 32767) truncated to 16 bits, no clipping). NULL = none */
