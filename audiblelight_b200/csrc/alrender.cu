@@ -110,6 +110,7 @@ struct alr_context {
   int fused_grid = 0;                     // resident CTAs of k_mov_fused (SMs x occupancy)
   int sm_clock_khz = 0;
   int mix_group = 0;                      // scenes per ambience-reduction + mixdown group (0: all at once)
+  long long watchdog_ms = 2000;           // ALR_WATCHDOG_MS: how long a persistent kernel may wait for one dependency
   int small_rir = 1;                      // k_small_rir for RIRs of at most one partition (ALR_SMALL=0: general pipeline)
   int64_t l2_persist_bytes = 0;           // L2 set aside for persisting lines (the ring of k_mov_sweep); 0: off
   int64_t l2_window_max = 0;
@@ -847,6 +848,7 @@ int alr_create(int device, alr_context** out) {
     if (const char* v = getenv("ALR_LOOKAHEAD")) ctx->lookahead = std::max(0, atoi(v));
     if (const char* v = getenv("ALR_MIX_GROUP")) ctx->mix_group = std::max(0, atoi(v));
     if (const char* v = getenv("ALR_SMALL")) ctx->small_rir = atoi(v) != 0;
+    if (const char* v = getenv("ALR_WATCHDOG_MS")) ctx->watchdog_ms = std::max(1LL, atoll(v));
   }
   *out = ctx;
   return ALR_OK;
@@ -1854,7 +1856,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         sa.xspec = d_xspec;
         sa.hring = (float2*)ctx->ring.p;
         sa.yspec = d_yspec;
-        sa.spin_limit = (long long)ctx->sm_clock_khz * 2000LL;
+        sa.spin_limit = (long long)ctx->sm_clock_khz * ctx->watchdog_ms;
         // Pin the ring in L2 for this launch: the taps (9 GB per benchmark step), X and Y stream through the same cache and
         // would otherwise push ring lines out between a producer's store and the sweepers' reads (56 % hit rate and 5 GB of
         // ring write-backs per launch without this, profiles/r02_sweep_v1.txt).
@@ -1898,7 +1900,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         fa.xspec = d_xspec;
         fa.hring = (float2*)ctx->ring.p;
         fa.yspec = d_yspec;
-        fa.spin_limit = (long long)ctx->sm_clock_khz * 2000LL;  // ~2 s of SM clocks
+        fa.spin_limit = (long long)ctx->sm_clock_khz * ctx->watchdog_ms;  // ~2 s of SM clocks
         k_mov_fused<<<std::min(ctx->fused_grid, ch.n_tasks), kCtaThreads, kFusedSmem, st>>>(fa);
         LAUNCH_CHECK(kCatFused);
       }

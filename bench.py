@@ -295,49 +295,98 @@ def main():
             sj.mix = torch.empty((sj.n_channels, sj.n_samples), dtype=torch.float32).pin_memory().numpy()
             h_jobs += j
             h_scenes.append(sj)
-        for _ in range(2):
-            rnd.render(h_jobs, h_scenes, stream)
-        barrier()
-        t0 = time.perf_counter()
-        h2d = d2h = 0
-        for _ in range(args.e2e_steps):
-            rnd.render(h_jobs, h_scenes, stream)  # pack + plan + H2D + kernels + D2H, synchronous
-            p = rnd.profile()
-            h2d, d2h = p["h2d_bytes"], p["d2h_bytes"]
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
         e2e_ss = sum(specs[i].duration for i in range(Se)) * world
-        e2e = {"value": e2e_ss * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "scenes_per_step_per_gpu": Se, "steps": args.e2e_steps,
-               "timing": "wall clock around Renderer.render (descriptor packing, planning, pinned H2D, kernels, D2H)",
-               "pcie_gbs": (h2d + d2h) * args.e2e_steps / dt / 1e9}
-        # the same step as dataset generation runs it (audiblelight_b200.dataset): only the 16-bit PCM of each mix
-        # is copied back; event.spatial_audio and the float mix stay on the device. Informational, not the headline.
+
+        def time_calls(fn, steps):
+            for _ in range(2):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            last = None
+            for _ in range(steps):
+                last = fn()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return dt, last
+
+        def one_call():
+            rnd.render(h_jobs, h_scenes, stream)  # pack + plan + H2D + kernels + D2H, synchronous
+            return rnd.profile()
+
+        def entry(dt, p, note):
+            return {"value": e2e_ss * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(p["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(p["d2h_bytes"]),
+                    "pcie_gbs": (p["h2d_bytes"] + p["d2h_bytes"]) * args.e2e_steps / dt / 1e9, "note": note}
+
+        # (1) every output of the C-ABI call comes back: all event.spatial_audio arrays and the mixes
+        dt, p = time_calls(one_call, args.e2e_steps)
+        all_outputs = entry(dt, p, "every event.spatial_audio (C, Lx) and every scene mix downloaded")
+        # (2) the step's RESULT is the scene mix (what Scene.generate writes, core.py:1840-1847): events are rendered and
+        # mixed on the device, scene.audio (float32) is the download. This is the headline e2e.
         for e in h_jobs:
             e.keep_spatial = False
+        dt, p = time_calls(one_call, args.e2e_steps)
+        e2e = entry(dt, p, "inputs (dry audio, RIRs, ambience) uploaded from pinned host memory, every scene mix (C, T) float32 "
+                           "downloaded; event audio is rendered and mixed on the device")
+        e2e.update({"scenes_per_step_per_gpu": Se, "steps": args.e2e_steps,
+                    "timing": "wall clock around Renderer.render (descriptor packing, planning, pinned H2D, kernels, D2H)",
+                    "all_outputs": all_outputs})
+        # (3) as dataset generation runs it (audiblelight_b200.dataset): only the 16-bit PCM of each mix is copied back
         for sj in h_scenes:
             sj.pcm16 = torch.empty((sj.n_samples, sj.n_channels), dtype=torch.int16).pin_memory().numpy()
             sj.keep_mix = False
-        for _ in range(2):
-            rnd.render(h_jobs, h_scenes, stream)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            rnd.render(h_jobs, h_scenes, stream)
-            p = rnd.profile()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e["dataset_mode"] = {"value": e2e_ss * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(p["h2d_bytes"]),
-                               "d2h_bytes_per_step": int(p["d2h_bytes"]),
-                               "note": "mix-only: PCM_16 (T, C) of every scene mix is the only download"}
+        dt, p = time_calls(one_call, args.e2e_steps)
+        e2e["dataset_mode"] = entry(dt, p, "mix-only: PCM_16 (T, C) of every scene mix is the only download")
+        # (4) two contexts, two host threads, alternating steps: the upload of step i + 1 overlaps the kernels and the
+        # download of step i (how audiblelight_b200.dataset drives batches). Same per-step work and copies as (2).
+        try:
+            import copy
+            import threading as _th
+            for sj in h_scenes:
+                sj.pcm16, sj.keep_mix = None, True
+            rnd_b = Renderer(local_rank)
+            jobs_b, scenes_b = copy.copy(h_jobs), []
+            jobs_b = [copy.copy(e) for e in h_jobs]
+            for sj in h_scenes:
+                sb = copy.copy(sj)
+                sb.mix = torch.empty((sj.n_channels, sj.n_samples), dtype=torch.float32).pin_memory().numpy()
+                scenes_b.append(sb)
+            streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+            work = [(rnd, h_jobs, h_scenes, streams[0]), (rnd_b, jobs_b, scenes_b, streams[1])]
+
+            def loop(k, n):
+                r_, j_, s_, st_ = work[k]
+                for _ in range(n):
+                    r_.render(j_, s_, st_.cuda_stream)
+
+            def both(n):
+                ts = [_th.Thread(target=loop, args=(k, n)) for k in range(2)]
+                for t_ in ts:
+                    t_.start()
+                for t_ in ts:
+                    t_.join()
+
+            both(1)
+            barrier()
+            t0 = time.perf_counter()
+            both(args.e2e_steps)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            e2e["two_contexts"] = {"value": e2e_ss * 2 * args.e2e_steps / dt, "unit": UNIT,
+                                   "note": "two renderer contexts driven by two host threads, steps alternate; per-step "
+                                           "copies as the headline e2e"}
+            rnd_b.close()
+            del jobs_b, scenes_b
+        except Exception as exc:
+            e2e["two_contexts"] = {"error": repr(exc)}
         del h_jobs, h_scenes
         # What a user of install() gets: the reference's own objects in, results on the objects out. float64 RIRs in
         # pageable numpy memory (as the reference's backends deliver them), converted to float32 by the host layer,
