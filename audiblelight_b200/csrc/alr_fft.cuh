@@ -4,8 +4,10 @@
 // (see below) and ONE P-point complex FFT done by a group of P/16 threads (16 elements each): Stockham autosort
 // passes of radix 16, 16 and P/256, butterflies in registers, two exchanges through shared memory.  This replaces
 // scipy's pocketfft calls of the reference (scipy.fft.rfft/irfft, synthesize.py:138,267; scipy.signal.fftconvolve,
-// :103,490).  P is a compile-time choice (-DALR_P=1024|2048|4096); 2048 measured best on the benchmark workload
-// (26.5 / 24.5 / 24.9 ms per step: larger partitions trade multiply-accumulates for FFT work, profiles/r01_partition_sweep.txt).
+// :103,490).  P is a compile-time choice (-DALR_P=1024|2048|4096). Benchmark step with the round-2 kernels: 24.5 / 21.8 /
+// 21.1 ms — larger partitions trade spectral multiply-accumulates (and spectra re-reads) for FFT work; round 1 measured
+// 26.5 / 24.5 / 24.9 and shipped 2048, the multiply-accumulate kernels have since gained more than the FFTs
+// (profiles/r01_partition_sweep.txt, profiles/r02_partition_sweep.txt). Default: 4096.
 //
 // Shared-memory layout: float2 elements, one pad element per 16 (index i -> i + i/16).  With 64-bit accesses the
 // hardware serves a warp as two half-warps of 16 lanes x 8 B; with this padding the stride-16 scatter of pass A
@@ -24,7 +26,7 @@
 namespace alr {
 
 #ifndef ALR_P
-#define ALR_P 2048
+#define ALR_P 4096
 #endif
 constexpr int kP = ALR_P;                    // partition length in samples == complex FFT size (1024, 2048 or 4096)
 static_assert(kP == 1024 || kP == 2048 || kP == 4096, "partition must be 1024, 2048 or 4096");

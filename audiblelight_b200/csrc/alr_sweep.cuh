@@ -40,21 +40,25 @@
 
 namespace alr {
 
-constexpr int kSwW = 15;             // accumulator window in output blocks (K + max xnb - 1 must fit)
+// Two layouts. P = 2048 (128-thread FFT groups): 16 sweeper warps on capsule pairs, 3 FFT groups, 15-block window.
+// P = 4096 (256-thread FFT groups): 8 sweeper warps with 4 capsules per thread, 2 FFT groups, 8-block window (a 1 s RIR
+// at 24 kHz is 6 partitions there).
+constexpr bool kSwWide = kGroup == 256;
+constexpr int kSwW = kSwWide ? 8 : 15;  // accumulator window in output blocks (K + max xnb - 1 must fit)
 constexpr int kSwMaxXnb = 4;         // source blocks per RIR held in registers
 constexpr int kSwStages = 6;         // pipeline depth (stages of 4 rows x 256 bins x 8 B)
 constexpr int kSwBins = 256;         // bins per sweeper CTA
-constexpr int kSwCapPerThread = 2;   // capsules per sweeper thread
+constexpr int kSwCapPerThread = kSwWide ? 4 : 2;   // capsules per sweeper thread
+constexpr bool kSwPipelined = kSwCapPerThread <= 2;  // software-pipelined loads need registers the 4-capsule layout lacks
 constexpr int kSwSweepThreads = kSwBins * (kChanGroup / kSwCapPerThread);  // 512
 constexpr int kSwSweepWarps = kSwSweepThreads / 32;
-constexpr int kSwGroups = 3;         // independent FFT groups of kGroup threads
+constexpr int kSwGroups = kSwWide ? 2 : 3;  // independent FFT groups of kGroup threads
 constexpr int kSwKSplit = 3;         // a (RIR, capsule) is produced as kSwKSplit P-tasks (partitions k = part, part + 3, ...):
                                      // shorter tasks, and the RIRs in production at any time fit the ring
 constexpr int kSwProdThreads = kSwGroups * kGroup;
 constexpr int kSwCopyWarp = (kSwSweepThreads + kSwProdThreads) / 32;
 constexpr int kSwThreads = kSwSweepThreads + kSwProdThreads + 32;  // 928 (29 warps, allocated as 32 x 64 registers)
 constexpr int kSwBinCtas = kP / kSwBins;                            // sweeper CTAs per event (8)
-static_assert(kChanGroup == 4 && kGroup == 128, "k_mov_sweep is laid out for 4 capsules and P = 2048");
 
 constexpr size_t kSwAccBytes = (size_t)kSwW * kChanGroup * kSwBins * sizeof(float2);                  // 122880
 constexpr size_t kSwStageBytes = (size_t)kChanGroup * kSwBins * sizeof(float2);                      // 8192
@@ -63,8 +67,10 @@ constexpr size_t kSwOffStage = kSwAccBytes;
 constexpr size_t kSwOffFft = kSwOffStage + kSwStages * kSwStageBytes;
 constexpr size_t kSwOffBar = kSwOffFft + kSwFftBytes;
 constexpr size_t kSwOffMisc = kSwOffBar + 2 * kSwStages * sizeof(unsigned long long);
-constexpr size_t kSwSmem = kSwOffMisc + 256;
-static_assert(kSwSmem <= 232448, "k_mov_sweep: shared memory over the 227 KB per-CTA limit");
+constexpr size_t kSwSmem = kSwOffMisc + 512;  // misc: 64 B per FFT group, scale slots at +256, fail flag at +320
+// laid out for 4 capsules per group and P = 2048 (128-thread FFT groups); other partition sizes build without it
+constexpr bool kSweepOk = kChanGroup == 4 && (kGroup == 128 || kGroup == 256) && kSwSmem <= 232448 &&
+                          kSwSweepThreads + kSwProdThreads + 32 <= 1024;
 
 struct SweepArgs {
   const EvDev* evs;
@@ -179,7 +185,7 @@ __device__ __forceinline__ int sweep_k_count(const EvDev& ev, const IrDev& ir) {
 __device__ __forceinline__ void sweep_copy_role(const SweepArgs& A, unsigned char* smem, int slot, int br) {
   unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + kSwOffBar);
   unsigned long long* empty = full + kSwStages;
-  float* sc_slot = reinterpret_cast<float*>(smem + kSwOffMisc + 128);
+  float* sc_slot = reinterpret_cast<float*>(smem + kSwOffMisc + 256);
   unsigned stage = 0, par = 1;  // waiting on an empty barrier's "previous" phase succeeds at once on the first lap
   long long w_empty = 0, w_ready = 0, n_stages = 0;
   const long long t_start = clock64();
@@ -247,7 +253,7 @@ __device__ __forceinline__ void sweep_consume_role(const SweepArgs& A, unsigned 
   float2* acc = reinterpret_cast<float2*>(smem);  // [w][c][bin]
   unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + kSwOffBar);
   unsigned long long* empty = full + kSwStages;
-  const float* sc_slot = reinterpret_cast<const float*>(smem + kSwOffMisc + 128);
+  const float* sc_slot = reinterpret_cast<const float*>(smem + kSwOffMisc + 256);
   const int tid = threadIdx.x, lane = tid & 31;
   const int lb = tid & (kSwBins - 1);                 // bin inside the CTA's slice
   const int c0 = (tid / kSwBins) * kSwCapPerThread;   // first of this thread's two capsules
@@ -264,7 +270,7 @@ __device__ __forceinline__ void sweep_consume_role(const SweepArgs& A, unsigned 
   // Only warp 0 polls the mbarrier; the other 15 warps join through a named barrier (a warp blocked in bar.sync costs no
   // issue slots, a warp blocked in mbarrier.try_wait is replayed by the hardware: with all 16 warps polling, a third of
   // the kernel's executed instructions were try_wait replays, profiles/r02_sweep.txt).
-  int* fail_flag = reinterpret_cast<int*>(smem + kSwOffMisc + 192);
+  int* fail_flag = reinterpret_cast<int*>(smem + kSwOffMisc + 320);
   auto wait_stage = [&]() -> bool {
 #if ALR_SWEEP_LEADER_WAIT
     if (tid < 32) {
@@ -351,17 +357,20 @@ __device__ __forceinline__ void sweep_consume_role(const SweepArgs& A, unsigned 
           for (int c = 0; c < kSwCapPerThread; ++c) dst[c] = (c < nc) ? st[c * kSwBins] : make_float2(0.f, 0.f);
           return true;
         };
-        if (!fetch(h)) return;
+        if (kSwPipelined && !fetch(h)) return;
         for (int k4 = 0; k4 < kn; k4 += 4) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             if (k4 + kk < kn) {
-              release();  // stage of step k: its values were requested a full step ago
-              if (k4 + kk + 1 < kn && !fetch(hn)) return;
+              if (!kSwPipelined && !fetch(h)) return;
+              release();  // stage of step k (pipelined: its values were requested a full step ago)
+              if (kSwPipelined && k4 + kk + 1 < kn && !fetch(hn)) return;
               float2* a = acc + (ws * kChanGroup + c0) * kSwBins + lb;
               float2 av[kSwCapPerThread];
+              if (kSwPipelined) {
 #pragma unroll
-              for (int c = 0; c < kSwCapPerThread; ++c) av[c] = (c < nc) ? a[c * kSwBins] : make_float2(0.f, 0.f);
+                for (int c = 0; c < kSwCapPerThread; ++c) av[c] = (c < nc) ? a[c * kSwBins] : make_float2(0.f, 0.f);
+              }
               // 4-tap FIR along k: X[j] * H[k] belongs to output block xb0 + k + j, held in z[.][(k + j) & 3]
 #pragma unroll
               for (int j = 0; j < kSwMaxXnb; ++j) {
@@ -378,12 +387,17 @@ __device__ __forceinline__ void sweep_consume_role(const SweepArgs& A, unsigned 
               // block xb0 + k is complete for this RIR: retire it into the window (it is < B by the choice of kn)
 #pragma unroll
               for (int c = 0; c < kSwCapPerThread; ++c) {
-                if (c < nc) a[c * kSwBins] = make_float2(av[c].x + z[c][kk].x, av[c].y + z[c][kk].y);
+                if (c < nc) {
+                  const float2 old = kSwPipelined ? av[c] : a[c * kSwBins];
+                  a[c * kSwBins] = make_float2(old.x + z[c][kk].x, old.y + z[c][kk].y);
+                }
                 z[c][kk] = make_float2(0.f, 0.f);
               }
               ws = (ws + 1 == kSwW) ? 0 : ws + 1;
+              if (kSwPipelined) {
 #pragma unroll
-              for (int c = 0; c < kSwCapPerThread; ++c) h[c] = hn[c];
+                for (int c = 0; c < kSwCapPerThread; ++c) h[c] = hn[c];
+              }
             }
           }
         }
@@ -427,7 +441,7 @@ __device__ __forceinline__ void sweep_consume_role(const SweepArgs& A, unsigned 
 // The P-task of alr_fused.cuh, run by ONE FFT group (128 threads, one transform in flight): the 64-register budget next
 // to the sweeper rules out two transforms per thread, and independent groups need no barrier wider than the FFT's own.
 __device__ __forceinline__ void sweep_produce_role(const SweepArgs& A, unsigned char* smem, int grp, int t) {
-  int* misc = reinterpret_cast<int*>(smem + kSwOffMisc) + grp * 8;  // [0] ticket, [1] fail flag, [2..6) energy partials
+  int* misc = reinterpret_cast<int*>(smem + kSwOffMisc) + grp * 16;  // [0] ticket, [1] fail flag, [2..10) energy partials
   float* red = reinterpret_cast<float*>(misc + 2);
   const int bar = 1 + grp;  // the group's named barrier (also used inside the FFT)
   FftSmem* fs = reinterpret_cast<FftSmem*>(smem + kSwOffFft) + grp;
@@ -522,8 +536,8 @@ __device__ __forceinline__ void sweep_produce_role(const SweepArgs& A, unsigned 
   }
 }
 
-// 29 warps are allocated as 32: 32 x 32 x 64 registers fill the 64 K register file exactly
-__global__ void __launch_bounds__(kSwThreads, 1)
+// P = 2048: 29 warps are allocated as 32 -> 64 registers per thread; P = 4096: 25 warps as 28 -> 72
+__global__ void __launch_bounds__(kSweepOk ? kSwThreads : 32, 1)
 k_mov_sweep(const SweepArgs A) {
   extern __shared__ __align__(16) unsigned char sweep_smem[];
   unsigned long long* full = reinterpret_cast<unsigned long long*>(sweep_smem + kSwOffBar);
@@ -533,7 +547,7 @@ k_mov_sweep(const SweepArgs A) {
       mbar_init(full + kSwStages + s, kSwSweepWarps);  // one arrival per sweeper warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    *reinterpret_cast<int*>(sweep_smem + kSwOffMisc + 192) = 0;
+    *reinterpret_cast<int*>(sweep_smem + kSwOffMisc + 320) = 0;
   }
   __syncthreads();
   const int tid = threadIdx.x;

@@ -819,7 +819,7 @@ int alr_create(int device, alr_context** out) {
       int per_sm2 = 0;
       cudaError_t s1 = cudaFuncSetAttribute(k_mov_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSmem);
       cudaError_t s2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_mov_sweep, kSwThreads, kSwSmem);
-      if (s1 == cudaSuccess && s2 == cudaSuccess && per_sm2 >= 1 && sms >= kSwBinCtas) ctx->sweep_grid = sms;
+      if (kSweepOk && s1 == cudaSuccess && s2 == cudaSuccess && per_sm2 >= 1 && sms >= kSwBinCtas) ctx->sweep_grid = sms;
       else cudaGetLastError();
     }
     // Experiment (ALR_L2_PERSIST=1, off): pin the ring with a persisting access-policy window. Measured: k_mov_sweep
