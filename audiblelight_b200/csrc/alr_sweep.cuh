@@ -187,7 +187,7 @@ __device__ __forceinline__ void sweep_copy_role(const SweepArgs& A, unsigned cha
   unsigned long long* empty = full + kSwStages;
   float* sc_slot = reinterpret_cast<float*>(smem + kSwOffMisc + 256);
   unsigned stage = 0, par = 1;  // waiting on an empty barrier's "previous" phase succeeds at once on the first lap
-  long long w_empty = 0, w_ready = 0, n_stages = 0;
+  [[maybe_unused]] long long w_empty = 0, w_ready = 0, n_stages = 0;
   const long long t_start = clock64();
   auto acquire_stage = [&]() -> bool {  // the stage `stage` is free again
     SW_T0();
@@ -259,7 +259,7 @@ __device__ __forceinline__ void sweep_consume_role(const SweepArgs& A, unsigned 
   const int c0 = (tid / kSwBins) * kSwCapPerThread;   // first of this thread's two capsules
   const int bin = br * kSwBins + lb;
   unsigned stage = 0, par = 0;  // stage / phase parity of the next stage in sequence
-  long long w_full = 0, n_irs_done = 0;
+  [[maybe_unused]] long long w_full = 0, n_irs_done = 0;
   const long long t_start = clock64();
   auto next_stage = [&]() {
     if (++stage == kSwStages) {
@@ -270,7 +270,7 @@ __device__ __forceinline__ void sweep_consume_role(const SweepArgs& A, unsigned 
   // Only warp 0 polls the mbarrier; the other 15 warps join through a named barrier (a warp blocked in bar.sync costs no
   // issue slots, a warp blocked in mbarrier.try_wait is replayed by the hardware: with all 16 warps polling, a third of
   // the kernel's executed instructions were try_wait replays, profiles/r02_sweep.txt).
-  int* fail_flag = reinterpret_cast<int*>(smem + kSwOffMisc + 320);
+  [[maybe_unused]] int* fail_flag = reinterpret_cast<int*>(smem + kSwOffMisc + 320);
   auto wait_stage = [&]() -> bool {
 #if ALR_SWEEP_LEADER_WAIT
     if (tid < 32) {
@@ -446,7 +446,7 @@ __device__ __forceinline__ void sweep_produce_role(const SweepArgs& A, unsigned 
   const int bar = 1 + grp;  // the group's named barrier (also used inside the FFT)
   FftSmem* fs = reinterpret_cast<FftSmem*>(smem + kSwOffFft) + grp;
   const float2 zt = __ldg(A.zeta + t);
-  long long w_pop = 0, n_tasks_done = 0;
+  [[maybe_unused]] long long w_pop = 0, n_tasks_done = 0;
   const long long t_start = clock64();
   for (;;) {
     if (t == 0) {
