@@ -115,7 +115,8 @@ struct alr_context {
   int64_t l2_persist_bytes = 0;           // L2 set aside for persisting lines (the ring of k_mov_sweep); 0: off
   int64_t l2_window_max = 0;
   HostBuf stage, stage_out, stage_aug;
-  int64_t ws_limit = (int64_t)4 << 30;  // 4 GiB: 3 % faster than 2 GiB on the benchmark (fewer, fuller launches); 8 GiB adds 1 %
+  int64_t ws_limit = (int64_t)16 << 30;  // spectra workspace bound (device inputs). Benchmark step at 4 / 8 / 16 / 32 GiB: 21.2 / 20.7 /
+                                         // 20.3 / 20.5 ms (fewer, fuller launches; B200 has 180 GB). Only what a call needs is allocated.
   int profiling = 0;
   alr_profile prof{};
   std::vector<cudaEvent_t> ev_pool;

@@ -194,7 +194,8 @@ int alr_struct_size(int which);
 int alr_create(int device, alr_context** out);
 void alr_destroy(alr_context* ctx);
 
-/* Upper bound for the spectra workspace (bytes); work is cut into chunks that fit. Default 4 GiB (device inputs; host inputs use at most 512 MiB so that transfers pipeline). */
+/* Upper bound for the spectra workspace (bytes); work is cut into chunks that fit. Default 16 GiB (device inputs; host inputs
+ * use at most 512 MiB so that transfers pipeline). Only what a call needs is allocated. */
 int alr_set_workspace_limit(alr_context* ctx, int64_t bytes);
 /* Tuning switches (name, value); unknown names fail with ALR_ERR_INVALID.
  *   "fused"       how moving events are rendered. 0: k_ir_fft + k_ir_scale + k_cmac (RIR spectra through HBM);
