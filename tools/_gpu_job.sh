@@ -1,2 +1,6 @@
-B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'^(k_ir_fft|k_cmac|k_cmac_static|k_ifft_ola|k_x_fft|k_mix|k_amb_partial)$' -s 36 -c 12 --csv --log-file gpurun_out/r02_traffic.csv $B > gpurun_out/l.log 2>&1
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/b.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r02_bench_1gpu.json").read().strip().splitlines()[-1])
+print("value", round(d["value"]), "ms", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["value"]), "cpu", round(d["cpu_baseline"]["value"],1), "pipe", round(d["roofline"]["pipeline"]["frac"],3), "fp32", round(d["roofline"]["fp32"]["frac"],3), d["roofline"]["kernel"], round(d["roofline"]["frac"],3), "traffic", d["roofline"]["traffic"], "alg/launch", d["roofline"]["algorithmic_bytes_per_launch"], d["clocks"], d["gpu_launches"])
+PY
