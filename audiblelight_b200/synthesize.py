@@ -81,8 +81,11 @@ def _valid_audio(y: np.ndarray) -> None:
     y = np.asarray(y)
     if not np.issubdtype(y.dtype, np.floating):
         raise ParameterError("Audio data must be floating-point")
-    if not np.isfinite(y).all():
-        raise ParameterError("Audio buffer is not finite everywhere")
+    # one pass, no temporary: a NaN or an infinity anywhere makes the float64 sum non-finite (inf - inf = nan), and a
+    # float64 sum of finite float32 / float64 audio cannot overflow for any buffer that fits in memory
+    if y.size and not np.isfinite(np.sum(y, dtype=np.float64)):
+        if not np.isfinite(y).all():  # (float64 input with values near 1e308 could overflow the sum: settle it exactly)
+            raise ParameterError("Audio buffer is not finite everywhere")
 
 
 def _validate_shape(shape_a, shape_b) -> None:
@@ -112,6 +115,24 @@ def _check_stft_geometry(fft_size, win_size, hop_size) -> None:
 _CONVERT_POOL = None
 
 
+def _convert_pool():
+    """Small thread pool for the big dtype conversions of a batch (numpy releases the GIL while it copies)."""
+    global _CONVERT_POOL
+    if _CONVERT_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        _CONVERT_POOL = ThreadPoolExecutor(max_workers=max(1, min(16, (os.cpu_count() or 2) - 1)))
+    return _CONVERT_POOL
+
+
+def _to_f64_many(arrays):
+    """float32 -> float64 copies of a batch of result arrays (what the reference stores in event.spatial_audio), in parallel."""
+    arrays = list(arrays)
+    if sum(a.size for a in arrays) < (1 << 22):
+        return [a.astype(np.float64) for a in arrays]
+    return list(_convert_pool().map(lambda a: a.astype(np.float64), arrays))
+
+
 def _as_f32(a, pool=None) -> np.ndarray:
     """C-contiguous float32 copy (no copy if it already is one). The reference's backends deliver float64 RIRs
     (worldstate.py:2210-2212): for a batch of scenes this conversion is the largest host cost of the drop-in, so
@@ -130,21 +151,16 @@ def _as_f32(a, pool=None) -> np.ndarray:
         if a.ndim == 0 or a.size < (1 << 21):
             return np.ascontiguousarray(a, dtype=np.float32)
         out = np.empty(a.shape, dtype=np.float32)
-    global _CONVERT_POOL
-    if _CONVERT_POOL is None:
-        from concurrent.futures import ThreadPoolExecutor
-        import os
-        _CONVERT_POOL = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
     axis = int(np.argmax(a.shape))
     n = a.shape[axis]
-    parts = min(8, n)
+    parts = min(16, n)
     bounds = [n * k // parts for k in range(parts + 1)]
 
     def conv(k):
         sl = [slice(None)] * a.ndim
         sl[axis] = slice(bounds[k], bounds[k + 1])
         np.copyto(out[tuple(sl)], a[tuple(sl)], casting="same_kind")
-    list(_CONVERT_POOL.map(conv, range(parts)))
+    list(_convert_pool().map(conv, range(parts)))
     return out
 
 
@@ -240,14 +256,17 @@ def _event_job(event, irs: np.ndarray, ref_db, ignore_cache: bool, pool=None) ->
     return job
 
 
-def _store_event_result(event, job: EventJob, mic_alias: str) -> None:
+def _store_event_result(event, job: EventJob, mic_alias: str, spatial64=None) -> None:
     n_ch, n_audio = job.n_channels, job.audio.shape[0]
     if job.stats["nonfinite"]:
         raise ParameterError("Audio buffer is not finite everywhere")
     if job.audio_out is not None:  # device-side augmentation: what Event.load_audio would have cached (event.py:538)
         _valid_audio(job.audio_out)
         event.audio = job.audio_out
-    spatial = job.spatial.astype(np.float64) if job.irs is not None else job.spatial  # N == 0 stays float32 (:577)
+    if job.irs is None:
+        spatial = job.spatial  # N == 0 stays float32 (:577)
+    else:
+        spatial = spatial64 if spatial64 is not None else job.spatial.astype(np.float64)
     _validate_shape(spatial.shape, (n_ch, n_audio))
     event.spatial_audio[mic_alias] = spatial
     if job.dry is not None:
@@ -535,12 +554,15 @@ def render_scenes(scenes: Sequence, ignore_cache: bool = True, device: int = -1,
     start = time()
     rnd.render(all_jobs, all_scenes)
     packed = {id(scene): OrderedDict() for scene in scenes}
+    # float64 copies of every rendered event in one parallel pass (the single largest host cost after the RIR conversion)
+    to64 = [j for _, _, _, mic_jobs, _ in book for j in mic_jobs if not j.prerendered and j.keep_spatial and j.irs is not None]
+    as64 = dict(zip((id(j) for j in to64), _to_f64_many(j.spatial for j in to64)))
     for scene, mic_alias, sjob, mic_jobs, placements in book:
         for j, (event, s0, s1) in zip(mic_jobs, placements):
             if j.stats is not None and j.stats["nonfinite"]:
                 raise ParameterError("Audio buffer is not finite everywhere")
             if not j.prerendered and j.keep_spatial:
-                _store_event_result(event, j, mic_alias)
+                _store_event_result(event, j, mic_alias, as64.get(id(j)))
             if store_padded and s1 > s0:
                 _store_padded(event, mic_alias, event.spatial_audio[mic_alias], s0, s1, sjob.n_channels,
                               sjob.n_samples, event._spatial_audio_dry.get(mic_alias))
