@@ -64,6 +64,8 @@ SYMBOLS = [
     ("alr_render", C.c_int, [C.c_void_p, C.POINTER(AlrEvent), C.c_int64, C.POINTER(AlrScene), C.c_int64, C.c_int,
                              C.POINTER(AlrEventStats), C.c_void_p]),
     ("alr_get_profile", C.c_int, [C.c_void_p, C.POINTER(AlrProfile)]),
+    ("alr_visibilities", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_int32,
+                                   C.c_double, C.c_int32, C.c_double, C.c_void_p, C.c_int, C.c_void_p]),
     ("alr_partition_size", C.c_int, []),
     ("alr_pinned_alloc", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     ("alr_pinned_free", None, [C.c_void_p, C.c_void_p]),

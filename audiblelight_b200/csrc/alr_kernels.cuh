@@ -1590,6 +1590,53 @@ k_amb_gauss(const GenDev* __restrict__ gens, float* __restrict__ peaks) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// f4: STFT / visibility front-end of acoustic imaging (imaging.py:455-719). A band's "collapsed spectrum" is the sum of a
+// few DFT bins of a windowed frame, i.e. ONE complex dot product of the frame with the modulated window
+// g_b[n] = w[n] sum_k exp(-2 pi i k n / N): no FFT of the (non power-of-two) frame length is needed.
+// grid = (frames, bands * channels), 64 threads; S[(f * n_bands + b) * C + c]
+__global__ void __launch_bounds__(64)
+k_vis_spectrum(const float* __restrict__ mix, long long T, int C, int N, int n_bands, const double2* __restrict__ g,
+               double2* __restrict__ S) {
+  __shared__ double s_re[2], s_im[2];
+  const int f = blockIdx.x, b = blockIdx.y / C, c = blockIdx.y % C;
+  const float* __restrict__ x = mix + (long long)c * T + (long long)f * N;
+  const double2* __restrict__ gb = g + (long long)b * N;
+  double re = 0.0, im = 0.0;
+  for (int n = threadIdx.x; n < N; n += 64) {
+    const double v = (double)__ldg(x + n);
+    const double2 w = gb[n];
+    re = fma(v, w.x, re);
+    im = fma(v, w.y, im);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    re += __shfl_xor_sync(0xffffffffu, re, o);
+    im += __shfl_xor_sync(0xffffffffu, im, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_re[threadIdx.x >> 5] = re;
+    s_im[threadIdx.x >> 5] = im;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) S[((long long)f * n_bands + b) * C + c] = make_double2(s_re[0] + s_re[1], s_im[0] + s_im[1]);
+}
+// grid = (blocks, bands), C*C threads (strided); V[((blk * n_bands + b) * C + i) * C + j] = sum_f conj(S_i) S_j
+__global__ void k_vis_outer(const double2* __restrict__ S, int C, int n_bands, int per_block, double2* __restrict__ V) {
+  const int blk = blockIdx.x, b = blockIdx.y;
+  for (int ij = threadIdx.x; ij < C * C; ij += blockDim.x) {
+    const int i = ij / C, j = ij % C;
+    double re = 0.0, im = 0.0;
+    for (int q = 0; q < per_block; ++q) {
+      const long long f = (long long)blk * per_block + q;
+      const double2 a = S[(f * n_bands + b) * C + i], bb = S[(f * n_bands + b) * C + j];
+      re += a.x * bb.x + a.y * bb.y;   // conj(a) * bb
+      im += a.x * bb.y - a.y * bb.x;
+    }
+    V[(((long long)blk * n_bands + b) * C + i) * C + j] = make_double2(re, im);
+  }
+}
+
 // ---- unit-test kernels for the FFT core ---------------------------------------------------------------------
 __global__ void __launch_bounds__(kCtaThreads)
 k_debug_rfft(const float* __restrict__ in, long long n_blocks, long long in_stride, int n_valid,

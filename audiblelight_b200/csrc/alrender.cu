@@ -100,7 +100,7 @@ struct alr_context {
   float2* d_tw = nullptr;    // exp(-2 pi i m / P), m < P
   float2* d_zeta = nullptr;  // exp(+i pi t / 2P), t < 64 (twist seed of thread t)
   float* d_win = nullptr;  // sin^2(pi p / 256), p < 128
-  DevBuf spec, desc, misc, arena, augbuf, augdesc, ring, ambgen;
+  DevBuf spec, desc, misc, arena, augbuf, augdesc, ring, ambgen, visbuf;
   // persistent producer/consumer launch for moving events (alr_fused.cuh)
   int fused = 0;                          // moving events: 0 = k_ir_fft + k_cmac, 1 = k_mov_fused (alr_fused.cuh, experiment,
                                           // profiles/r02_fused_ring.txt), 2 = k_mov_sweep (alr_sweep.cuh)
@@ -870,6 +870,7 @@ void alr_destroy(alr_context* ctx) {
   ctx->augdesc.release();
   ctx->ring.release();
   ctx->ambgen.release();
+  ctx->visbuf.release();
   ctx->stage.release();
   ctx->stage_out.release();
   ctx->stage_aug.release();
@@ -2034,6 +2035,84 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
       stats_out[i].dry_peak = events_in[i].dry ? hs[i].dry_peak : -1;
     }
   }
+  return ALR_OK;
+}
+
+int alr_visibilities(alr_context* ctx, const float* mix, int32_t n_channels, int64_t n_samples, double rate, double t_sti,
+                     const double* fc, int32_t n_bands, double bw, int32_t n_sti_per_block, double tukey_alpha,
+                     double* out, int mem_space, void* stream) {
+  if (!ctx || !mix || !fc || !out) return fail(ALR_ERR_INVALID, "alr_visibilities: NULL argument");
+  if (mem_space != ALR_MEM_HOST && mem_space != ALR_MEM_DEVICE) return fail(ALR_ERR_INVALID, "alr_visibilities: bad mem_space");
+  if (n_channels < 1 || n_channels > 1024 || n_samples < 1 || n_bands < 1 || n_sti_per_block < 1 || !(rate > 0) || !(t_sti > 0))
+    return fail(ALR_ERR_INVALID, "alr_visibilities: bad shape");
+  const long long N = (long long)(rate * t_sti);  // int(rate_ * t), imaging.py:467
+  if (N == 0) return fail(ALR_ERR_INVALID, "Not enough samples per time frame.");  // imaging.py:469
+  if (N > 0x3fffffff) return fail(ALR_ERR_INVALID, "alr_visibilities: frame too long");
+  const long long n_stf = n_samples / N, n_blocks = n_stf / n_sti_per_block;
+  if (n_blocks < 1) return ALR_OK;  // nothing to write
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = n_channels;
+  // modulated windows, float64: g[b][n] = tukey(n) * sum_{k in band b} exp(-2 pi i k n / N)
+  std::vector<double> win((size_t)N);
+  {
+    // scipy.signal.windows.tukey(M, alpha, sym=True)
+    const long long M = N;
+    if (tukey_alpha <= 0.0 || M == 1) {
+      for (long long n = 0; n < M; ++n) win[n] = 1.0;
+    } else if (tukey_alpha >= 1.0) {
+      for (long long n = 0; n < M; ++n) win[n] = 0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)(M - 1));  // hann(M, sym=True)
+    } else {
+      const long long width = (long long)floor(tukey_alpha * (double)(M - 1) / 2.0);
+      for (long long n = 0; n < M; ++n) {
+        if (n <= width) win[n] = 0.5 * (1.0 + cos(M_PI * (-1.0 + 2.0 * (double)n / tukey_alpha / (double)(M - 1))));
+        else if (n < M - width - 1) win[n] = 1.0;
+        else win[n] = 0.5 * (1.0 + cos(M_PI * (-2.0 / tukey_alpha + 1.0 + 2.0 * (double)n / tukey_alpha / (double)(M - 1))));
+      }
+    }
+  }
+  std::vector<double2> g((size_t)n_bands * N);
+  for (int b = 0; b < n_bands; ++b) {
+    // bins stft_data[:, idx_start : idx_end + 1] with Python slice semantics (imaging.py:485-487)
+    long long i0 = (long long)((fc[b] - 0.5 * bw) * (double)N / rate), i1 = (long long)((fc[b] + 0.5 * bw) * (double)N / rate) + 1;
+    if (i0 < 0) i0 = std::max<long long>(i0 + N, 0);
+    if (i1 < 0) i1 = std::max<long long>(i1 + N, 0);
+    i0 = std::min(i0, N);
+    i1 = std::min(i1, N);
+    for (long long n = 0; n < N; ++n) {
+      double re = 0.0, im = 0.0;
+      for (long long k = i0; k < i1; ++k) {
+        const double ph = -2.0 * M_PI * (double)((k * n) % N) / (double)N;
+        re += cos(ph);
+        im += sin(ph);
+      }
+      g[(size_t)b * N + n] = make_double2(win[n] * re, win[n] * im);
+    }
+  }
+  const size_t off_g = 0, bytes_g = g.size() * sizeof(double2);
+  const size_t off_s = align_up(off_g + bytes_g, 256), bytes_s = (size_t)n_stf * n_bands * C * sizeof(double2);
+  const size_t off_v = align_up(off_s + bytes_s, 256), bytes_v = (size_t)n_blocks * n_bands * C * C * sizeof(double2);
+  const size_t off_x = align_up(off_v + bytes_v, 256), bytes_x = mem_space == ALR_MEM_HOST ? (size_t)C * n_samples * sizeof(float) : 0;
+  int rc = ctx->visbuf.ensure(off_x + bytes_x + 256);
+  if (rc) return rc;
+  char* base = (char*)ctx->visbuf.p;
+  CUDA_TRY(cudaMemcpyAsync(base + off_g, g.data(), bytes_g, cudaMemcpyHostToDevice, st));
+  const float* d_mix = mix;
+  if (mem_space == ALR_MEM_HOST) {
+    CUDA_TRY(cudaMemcpyAsync(base + off_x, mix, bytes_x, cudaMemcpyHostToDevice, st));
+    d_mix = (const float*)(base + off_x);
+  }
+  if (n_stf > 0x7fffffffLL || (long long)n_bands * C > 65535)
+    return fail(ALR_ERR_INVALID, "alr_visibilities: too many frames or band x channel pairs");
+  k_vis_spectrum<<<dim3((unsigned)n_stf, (unsigned)(n_bands * C)), 64, 0, st>>>(d_mix, n_samples, C, (int)N, n_bands,
+                                                                                (const double2*)(base + off_g),
+                                                                                (double2*)(base + off_s));
+  CUDA_TRY(cudaGetLastError());
+  k_vis_outer<<<dim3((unsigned)n_blocks, (unsigned)n_bands), std::min(C * C, 256), 0, st>>>(
+      (const double2*)(base + off_s), C, n_bands, n_sti_per_block, (double2*)(base + off_v));
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, base + off_v, bytes_v, mem_space == ALR_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return ALR_OK;
 }
 

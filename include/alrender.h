@@ -229,6 +229,23 @@ int alr_render(alr_context* ctx, const alr_event* events, int64_t n_events, cons
 
 int alr_get_profile(alr_context* ctx, alr_profile* out);
 
+/*
+ * f4, a consumer of the mix: the STFT / visibility front-end of acoustic imaging — extract_visibilities + form_visibility
+ * (imaging.py:455-719) for all frequency bands of get_visibility_matrix (:775-853) in one call.
+ *   mix        (C, T) float32 = scene.audio[mic]  (the reference passes its transpose, (samples, channels))
+ *   N = int(rate * t_sti) samples per short-time frame, n_stf = T / N frames, each multiplied with a Tukey(alpha) window
+ *   (scipy.signal.windows.tukey, sym=True; alpha = 1 in form_visibility) and transformed with an N-point DFT; per band b
+ *   the bins [int((fc[b] - bw/2) N / rate), int((fc[b] + bw/2) N / rate)] (Python slice semantics) are summed to one
+ *   complex value per channel, S[f, b, c]; the visibility of a stationarity block of n_sti_per_block frames is
+ *   V[blk, b, i, j] = sum_f conj(S[f, b, i]) S[f, b, j].
+ *   out        (n_blocks, n_bands, C, C) complex128 as (re, im) float64 pairs, n_blocks = n_stf / n_sti_per_block.
+ * Only the needed bins are evaluated (one modulated window per band, built in float64 on the host), accumulation is
+ * float64. mem_space tells where mix and out live.
+ */
+int alr_visibilities(alr_context* ctx, const float* mix, int32_t n_channels, int64_t n_samples, double rate, double t_sti,
+                     const double* fc, int32_t n_bands, double bw, int32_t n_sti_per_block, double tukey_alpha,
+                     double* out, int mem_space, void* stream);
+
 /* ---- unit-test hooks for the FFT core (device pointers) -------------------------------------------------
  * Forward: n_blocks real blocks of `n_valid` (<= partition) samples each, implicitly zero-padded to 2*partition,
  * through the negacyclic fold + twist transform of the kernels (csrc/alr_fft.cuh): `partition` ordinary complex
