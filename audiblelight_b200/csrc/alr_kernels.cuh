@@ -361,6 +361,10 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -412,6 +416,12 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
   // at a 10 % L2 hit rate); with alternating directions runs r and r+1 reach the shared items at the same end of their
   // lists. Measured: k_cmac 5.80 -> 6.04 ms per benchmark step: CTAs of neighbouring runs do not stay in step, so the
   // second read still misses L2, and the descending walk is slower on its own (profiles/r01_cmac_variants.txt).
+// H staging of k_cmac: 1 = 16-byte cp.async.cg copies, a warp owns its slice of a stage (the north star's "coalesced float4
+// loads" of the spectra; half the LDGSTS instructions, L1 bypassed for data that is read once per CTA); 0 = round 1's 8-byte
+// copies with thread-private stages. Measured equal within noise (k_cmac 4.98 vs 4.99 ms per benchmark step).
+#ifndef ALR_CMAC_COPY16
+#define ALR_CMAC_COPY16 1
+#endif
 #ifndef ALR_CMAC_ZIGZAG
 #define ALR_CMAC_ZIGZAG 0
 #endif
@@ -463,10 +473,22 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
     };
     auto produce = [&](int stage) {
       if (prod_ok) {
+#if ALR_CMAC_COPY16
+        // 16-byte copies ("float4 loads" of the spectra): the warp's 4 x 32-bin slice of an item is 64 pieces of 16 bytes, two
+        // per lane (capsule = piece / 16, bin pair = piece % 16); a stage is then warp-private instead of thread-private
+        float2* dst = &ring[stage][0][(tid & ~31) + (tid & 15) * 2];
+        const float2* src = php - tid + (tid & ~31) + (tid & 15) * 2;  // php points at this thread's own bin
+#pragma unroll
+        for (int q = 0; q < kChanGroup / 2; ++q) {
+          const int c = ((tid >> 4) & 1) + 2 * q;
+          if (c < nc) cp_async16(dst + c * kCtaThreads, src + c * kP);
+        }
+#else
         float2* dst = ring_t + stage * (kChanGroup * kCtaThreads);
 #pragma unroll
         for (int c = 0; c < kChanGroup; ++c)
           if (c < nc) cp_async8(dst + c * kCtaThreads, php + c * kP);
+#endif
         prod_advance();
       }
       cp_async_commit();  // (possibly empty) group: keeps the group count in step with the item count
@@ -499,12 +521,22 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
     for (int i = 0; i < kStages - 1; ++i) produce(i);
     int stage = 0;
     while (cons_ok) {
+#if ALR_CMAC_COPY16
+      cp_async_wait<kStages - 2>();  // this lane's pieces of the consumer's item have landed ...
+      __syncwarp();                  // ... and the other lanes'; every lane is done with the previous stage
+      const float2* src = ring_t + stage * (kChanGroup * kCtaThreads);
+      float2 h[kChanGroup];
+#pragma unroll
+      for (int c = 0; c < kChanGroup; ++c) h[c] = (c < nc) ? src[c * kCtaThreads] : make_float2(0.f, 0.f);
+      produce(stage == 0 ? kStages - 1 : stage - 1);  // refill the slot consumed in the previous iteration
+#else
       produce(stage == 0 ? kStages - 1 : stage - 1);  // refill the slot consumed in the previous iteration
       cp_async_wait<kStages - 1>();                    // the consumer's item has landed
       const float2* src = ring_t + stage * (kChanGroup * kCtaThreads);
       float2 h[kChanGroup];
 #pragma unroll
       for (int c = 0; c < kChanGroup; ++c) h[c] = (c < nc) ? src[c * kCtaThreads] : make_float2(0.f, 0.f);
+#endif
       // outputs s with 0 <= s + jb < xnb and s < nb
       const int s_lo = max(0, -cjb);
       const unsigned s_cnt = (unsigned)max(0, min(nb, cxnb - cjb) - s_lo);
