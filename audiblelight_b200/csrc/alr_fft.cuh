@@ -23,6 +23,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Cache hints for spectra that are written by one kernel and read once by the next (far larger than L2):
+// ALR_STREAM_SPECTRA=1 uses streaming (evict-first) stores / loads.
+#ifndef ALR_STREAM_SPECTRA
+#define ALR_STREAM_SPECTRA 0
+#endif
+#if ALR_STREAM_SPECTRA
+#define ALR_SPEC_STORE(p, v) __stcs((p), (v))
+#define ALR_SPEC_LOAD(p) __ldcs((p))
+#else
+#define ALR_SPEC_STORE(p, v) (*(p) = (v))
+#define ALR_SPEC_LOAD(p) (*(p))
+#endif
+
 namespace alr {
 
 #ifndef ALR_P
@@ -315,7 +328,7 @@ __device__ __forceinline__ void fwd_block_to_global(const float (&a)[16], float2
 #pragma unroll
   for (int m = 0; m < kM3; ++m)
 #pragma unroll
-    for (int k = 0; k < kR3; ++k) spec[t + kGroup * m + 256 * k] = o[m][k];
+    for (int k = 0; k < kR3; ++k) ALR_SPEC_STORE(spec + t + kGroup * m + 256 * k, o[m][k]);
   group_sync(bar);  // pass-C gathers done before the next transform's scatter
 }
 
@@ -351,7 +364,7 @@ __device__ __forceinline__ void inv_block_from_global(const float2* __restrict__
                                                       float2 (&o)[kM3][kR3]) {
   float2 v[16];
 #pragma unroll
-  for (int r = 0; r < 16; ++r) v[r] = spec[t + kGroup * r];
+  for (int r = 0; r < 16; ++r) v[r] = ALR_SPEC_LOAD(spec + t + kGroup * r);
   fft_core<true>(v, s, tw, t, bar, o);
   const float2 ztc = cconj(zt);
 #pragma unroll

@@ -574,7 +574,7 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
     if (s < nb)
 #pragma unroll
       for (int c = 0; c < kChanGroup; ++c)
-        if (c < nc) yspec[(ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin] = acc[s][c];
+        if (c < nc) ALR_SPEC_STORE(yspec + (ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin, acc[s][c]);
 }
 
 // k_cmac_static: the same contraction for STATIC events (one IR, every source block active), where it is a plain
@@ -709,7 +709,7 @@ k_cmac_static(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ p
 #if ALR_FFMA2
         if (c < nc) yspec[(ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin] = unpack2(acc[s][c]);
 #else
-        if (c < nc) yspec[(ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin] = acc[s][c];
+        if (c < nc) ALR_SPEC_STORE(yspec + (ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin, acc[s][c]);
 #endif
 }
 
