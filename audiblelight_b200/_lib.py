@@ -71,6 +71,8 @@ SYMBOLS = [
     ("alr_pinned_free", None, [C.c_void_p, C.c_void_p]),
     ("alr_debug_rfft", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     ("alr_debug_irfft", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    ("alr_debug_plan_movers", C.c_int, [C.POINTER(AlrEvent), C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     ("alr_debug_plan", C.c_int, [C.POINTER(AlrEvent), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                  C.c_void_p, C.c_int64]),
 ]

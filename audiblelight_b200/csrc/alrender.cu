@@ -2116,6 +2116,84 @@ int alr_visibilities(alr_context* ctx, const float* mix, int32_t n_channels, int
   return ALR_OK;
 }
 
+int alr_debug_plan_movers(const alr_event* events, int32_t n_events, int32_t mode, int64_t ring_bytes, int32_t lookahead,
+                          int32_t n_slots, int32_t* header, int32_t* tasks, int64_t tasks_cap, int32_t* per_ir,
+                          int64_t per_ir_cap) {
+  if (!events || n_events < 1 || !header || !tasks || !per_ir || (mode != 1 && mode != 2))
+    return fail(ALR_ERR_INVALID, "alr_debug_plan_movers: bad argument");
+  const long long ring_slots = ring_bytes / ((int64_t)kP * sizeof(float2));
+  std::vector<EvSize> sz(n_events);
+  int n_ir = 0, n_w = 0, n_blk = 0, n_fo = 0, n_tasks = 0, n_sweep_ev = 0;
+  for (int i = 0; i < n_events; ++i) {
+    int rc = size_event(events[i], i, sz[i], ring_slots, mode, 0);
+    if (rc) return rc;
+    n_ir += sz[i].n_ir;
+    n_w += sz[i].wband;
+    n_blk += sz[i].n_blk;
+    if (sz[i].fused) {
+      n_fo += sz[i].n_ir;
+      n_tasks += sz[i].n_ptask + sz[i].n_ctask;
+      n_sweep_ev += sz[i].fused == 2;
+    }
+  }
+  std::vector<EvDev> evs(n_events);
+  std::vector<IrDev> irs(std::max(n_ir, 1));
+  std::vector<float> wband(std::max(n_w, 1));
+  std::vector<int2> lr(std::max(n_blk, 1));
+  int ir_off = 0, w_off = 0, blk_off = 0;
+  for (int i = 0; i < n_events; ++i) {
+    int x_used = 0;
+    plan_event_into(events[i], i, sz[i], evs[i], irs.data() + ir_off, ir_off, wband.data() + w_off, w_off, lr.data() + blk_off,
+                    blk_off, &x_used);
+    evs[i].fused = sz[i].fused;
+    ir_off += sz[i].n_ir;
+    w_off += sz[i].wband;
+    blk_off += sz[i].n_blk;
+  }
+  header[0] = n_fo;
+  header[1] = n_tasks;
+  header[2] = (int)std::min<long long>(ring_slots, 0x7fffffff);
+  header[3] = 0;
+  for (int i = 0; i < n_events; ++i) header[3] += sz[i].fused != 0;
+  if (n_fo == 0) return ALR_OK;
+  if ((int64_t)n_tasks * 4 > tasks_cap || (int64_t)n_fo * 10 > per_ir_cap)
+    return fail(ALR_ERR_INVALID, "alr_debug_plan_movers: output buffers too small (%d tasks, %d RIRs)", n_tasks, n_fo);
+  std::vector<FusedTask> tk(n_tasks);
+  std::vector<int2> pop(n_fo), need(n_fo);
+  std::vector<int> prod(n_fo, -1), slot_off(kMaxSweepSlots + 1), slot_jobs(std::max(n_sweep_ev, 1));
+  int slots_used = 0;
+  bool ok;
+  if (mode == 1) {
+    ok = plan_fused(evs.data(), n_events, irs.data(), lr.data(), ring_slots, lookahead, tk.data(), n_tasks, pop.data(), need.data(), n_fo);
+    for (int i = 0; i < n_fo; ++i) prod[i] = i;  // ordinal == production order
+  } else {
+    ok = plan_sweep(evs.data(), n_events, irs.data(), ring_slots, std::max(1, std::min(n_slots, kMaxSweepSlots)), tk.data(), n_tasks,
+                    pop.data(), need.data(), prod.data(), n_fo, slot_off.data(), slot_jobs.data(), n_sweep_ev, &slots_used);
+  }
+  if (!ok) return fail(ALR_ERR_INVALID, "internal: inconsistent plan");
+  header[4] = slots_used;
+  for (int i = 0; i < n_tasks; ++i) {
+    tasks[4 * i] = tk[i].type;
+    tasks[4 * i + 1] = tk[i].ev;
+    tasks[4 * i + 2] = tk[i].idx;
+    tasks[4 * i + 3] = tk[i].sub;
+  }
+  std::vector<int> prod_index(n_fo, -1);
+  for (int p2 = 0; p2 < n_fo; ++p2)
+    if (prod[p2] >= 0) prod_index[prod[p2]] = p2;
+  for (int e = 0; e < n_events; ++e) {
+    if (!evs[e].fused) continue;
+    for (int l = 0; l < evs[e].N; ++l) {
+      const int fo = evs[e].fo0 + l;
+      int32_t* o = per_ir + 10 * fo;
+      o[0] = e; o[1] = l; o[2] = irs[evs[e].ir0 + l].hring; o[3] = evs[e].K * evs[e].C;
+      o[4] = pop[fo].x; o[5] = pop[fo].y; o[6] = need[fo].x; o[7] = need[fo].y; o[8] = prod_index[fo];
+      o[9] = (mode == 1) ? 0 : irs[evs[e].ir0 + l].xnb;
+    }
+  }
+  return ALR_OK;
+}
+
 int alr_debug_rfft(alr_context* ctx, const float* in, int64_t n_blocks, int64_t in_stride, int32_t n_valid,
                    float* spec_out, void* stream) {
   if (!ctx || !in || !spec_out || n_blocks < 1 || n_valid < 0 || n_valid > kP)

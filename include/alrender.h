@@ -271,6 +271,16 @@ int alr_debug_irfft(alr_context* ctx, const float* spec_in, int64_t n_blocks, fl
 int alr_debug_plan(const alr_event* ev, int32_t* header, int32_t* irs, int64_t irs_cap, float* wband,
                    int64_t wband_cap, int32_t* lrange, int64_t lrange_cap);
 
+/* Host-only: the task queue / production plan of the persistent moving-event launches for a list of events
+ * (mode 1 = k_mov_fused, 2 = k_mov_sweep), for CPU tests of the planner's invariants.
+ *   header[5]   {fused RIRs, tasks, ring slots, fused events, sweeper slots used}
+ *   tasks       4 int32 per task: {type (0 P, 1 C), event, RIR | run, capsule | sub-tile}
+ *   per_ir      10 int32 per fused RIR ordinal: {event, l, ring slot, slots, pop_x, pop_y, readers, ready target,
+ *               production index, active source blocks}; pop_x / pop_y index production order */
+int alr_debug_plan_movers(const alr_event* events, int32_t n_events, int32_t mode, int64_t ring_bytes, int32_t lookahead,
+                          int32_t n_slots, int32_t* header, int32_t* tasks, int64_t tasks_cap, int32_t* per_ir,
+                          int64_t per_ir_cap);
+
 #ifdef __cplusplus
 }
 #endif
