@@ -34,8 +34,8 @@ constexpr int kIrTasks = ALR_IR_TASKS;               // RIR partitions transform
 constexpr int kChanGroup = ALR_CMAC_CH;              // capsules per k_cmac thread / CTA
 constexpr int kIfftCh = kGroupsPerCta;               // capsules per IFFT CTA (one FFT group each)
 #ifndef ALR_IFFT_RUN
-#define ALR_IFFT_RUN 8
-#endif
+#define ALR_IFFT_RUN 16  // at P = 4096: 8 / 16 / 32 blocks per run -> k_ifft_ola 1.96 / 1.87 / 1.89 ms per benchmark step (a run re-does the
+#endif                   // inverse transform of the block before it for the overlap tail: 1/16 extra work instead of 1/8)
 constexpr int kRun = ALR_IFFT_RUN;                              // consecutive output blocks per IFFT CTA (tail kept in registers)
 constexpr int kBinCtas = kP / kCtaThreads;           // CMAC CTAs per spectrum (each thread owns one bin)
 
