@@ -74,6 +74,27 @@ class ClockSampler:
         self._t = None
 
     def _loop(self):
+        # NVML (nvidia_ml_py) answers in well under a millisecond, so even a 0.4 s timed region gets dozens of samples;
+        # nvidia-smi (one process per sample, ~50-100 ms) is the fallback.
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            while not self._stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                row = [str(self.idx), str(sm), str(mx), "", hex(r)]
+                row += ["Active" if r & bits[n] else "Not Active"
+                        for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+                self.rows.append(row)
+                self._stop.wait(0.005)
+            return
+        except Exception:
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
