@@ -245,6 +245,10 @@ k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix,
         const float2* __restrict__ tw, const float2* __restrict__ zeta, const float* __restrict__ win,
         float2* __restrict__ xspec) {
   __shared__ FftSmem sm[kGroupsPerCta];
+  // cross-fade weights of the kP / 128 + 1 STFT frames a block touches, staged once per block: every thread needs 32 of them,
+  // and as predicated global loads they were the kernel's main stall (long scoreboard 7 per issue, profiles/r01_xfft_v4.txt)
+  constexpr int kFrames = kP / 128 + 1;
+  __shared__ float s_w[kGroupsPerCta][kFrames + 1];
   const int g = threadIdx.x / kGroup, t = threadIdx.x % kGroup, bar = 1 + g;
   // kXTasks consecutive source blocks per group: the two lookups (event, then IR inside the event: ~15 dependent
   // loads) are done once and then advanced incrementally
@@ -289,6 +293,13 @@ k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix,
       s_even = __ldg(win + (t & 127));
       s_odd = __ldg(win + ((t + 64) & 127));
     }
+    if (ev.moving) {  // (uniform over the group)
+      if (t <= kFrames) {
+        const int q = (t0 >> 7) - ir.jmin + t;  // row of the weight band for frame (t0 >> 7) + t
+        s_w[g][t] = (q >= 0 && q < ir.nrows && t < kFrames) ? __ldg(wband + ir.woff + q) : 0.f;
+      }
+      group_sync(bar);  // the previous block's reads of s_w finished before its transform's first barrier
+    }
     float a[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
@@ -296,9 +307,8 @@ k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix,
       float v = (n < ev.xlimit) ? __ldg(x + n) : 0.f;
       float gw = sc;
       if (ev.moving) {
-        const int q = (t0 >> 7) + ((t + kGroup * r) >> 7) - ir.jmin;  // STFT frame of sample n
-        const float w0 = (q >= 0 && q < ir.nrows) ? __ldg(wband + ir.woff + q) : 0.f;
-        const float w1 = (q + 1 >= 0 && q + 1 < ir.nrows) ? __ldg(wband + ir.woff + q + 1) : 0.f;
+        const int f = (t + kGroup * r) >> 7;  // STFT frame of sample n, relative to the block's first
+        const float w0 = s_w[g][f], w1 = s_w[g][f + 1];
         gw = sc * fmaf(w1 - w0, (kGroup == 64 && (r & 1)) ? s_odd : s_even, w0);  // w0 (1 - s) + w1 s
       }
       a[r] = v * gw;
