@@ -163,6 +163,8 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
   int e = find_segment(prefix, n_ev, task0);
   int seg_lo = __ldg(prefix + e), seg_hi = __ldg(prefix + e + 1);
   const float2 zt = __ldg(zeta + t);
+  int c = 0, k = 0, l = 0;
+  bool fresh = true;  // (c, k, l) must be derived from the task index: first task of the group or a new event
   for (int i = 0; i < kIrTasks; ++i) {
     const int task = task0 + i;
     if (task >= n_tasks) break;
@@ -170,13 +172,23 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
       ++e;
       seg_lo = seg_hi;
       seg_hi = __ldg(prefix + e + 1);
+      fresh = true;
     }
     const EvDev& ev = evs[e];
-    int local = task - seg_lo;
-    const int c = local % ev.C;
-    local /= ev.C;
-    const int k = local % ev.K;
-    const int l = local / ev.K;
+    if (fresh) {  // two integer divisions; the following tasks of the same event just count on
+      int local = task - seg_lo;
+      c = local % ev.C;
+      local /= ev.C;
+      k = local % ev.K;
+      l = local / ev.K;
+      fresh = false;
+    } else if (++c == ev.C) {
+      c = 0;
+      if (++k == ev.K) {
+        k = 0;
+        ++l;
+      }
+    }
     const float* __restrict__ src = ev.irs + (long long)c * ev.ir_stride_c + (long long)l * ev.ir_stride_n;
     const int t0 = k * kP;
     const int lo = max(ev.mask_lo, t0), hi = min(min(ev.mask_hi, ev.Lh), t0 + kP);
