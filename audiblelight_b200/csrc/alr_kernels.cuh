@@ -349,6 +349,10 @@ constexpr int kG = 8;       // output blocks per CTA (k_cmac_static)
 #define ALR_CMAC_STAGES 5
 #endif
 constexpr int kGm = ALR_CMAC_G;            // output blocks per CTA (k_cmac); even
+#ifndef ALR_CMAC_RUNS
+#define ALR_CMAC_RUNS 4
+#endif
+constexpr int kCmacRuns = ALR_CMAC_RUNS;  // consecutive runs of kGm output blocks one k_cmac CTA works through
 constexpr int kStages = ALR_CMAC_STAGES;  // cp.async ring depth: 5 x 4 capsules x 256 threads x 8 B = 40 KB
 
 // ---- packed fp32 pairs (Blackwell FFMA2, experiment): `fma.rn.f32x2` does two FMAs per instruction on a 64-bit
@@ -391,20 +395,27 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-struct CmacHead {  // one IR as seen by one CTA (run of output blocks): built once per CTA into shared memory
-  int k_lo, k_hi;    // partitions of the IR that contribute to the run (empty when k_lo > k_hi)
-  int d0, xnb;       // source block of output s and partition k: j = s + d0 - k, valid for 0 <= j < xnb
-  long long xoff;    // float2 offset of X_l[0] from the event's X base
-  long long hoff;    // float2 offset of H_l[k_lo][c0] from the event's H base
+// One (RIR l, partition k) item of a k_cmac CTA, built into shared memory before the pipeline runs (16 bytes, read with
+// one broadcast LDS.128): rows are in units of kP float2 elements.
+struct __align__(16) CmacItem {
+  int hrow;  // H_l[k][c0] relative to the event's first spectrum row of capsule c0: (l * K + k) * C
+  int xrow;  // X_l[j] of output 0 relative to the event's first source row: xslot_l + d0 - k (output s reads row xrow + s)
+  int mask;  // bit s: output s of the run takes this item (0 <= s + d0 - k < xnb, s < nb); bits 8.. see pfmask
+  int pfrow; // the one source row no earlier item of the RIR has touched (prefetched with the item's H copy)
 };
-constexpr int kMaxHeads = 64;
+constexpr int kMaxHeads = 64;   // RIRs per list-building window (one thread each)
+constexpr int kMaxItems = 448;  // list capacity (7 KB); longer windows are worked through in passes
+#ifndef ALR_CMAC_PF
+#define ALR_CMAC_PF 1
+#endif
 
 __global__ void __launch_bounds__(kCtaThreads, 2)
 k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const IrDev* __restrict__ irs,
        const int2* __restrict__ lrange, const float2* __restrict__ xspec, const float2* __restrict__ hspec,
        float2* __restrict__ yspec) {
   __shared__ float2 ring[kStages][kChanGroup][kCtaThreads];
-  __shared__ CmacHead heads[kMaxHeads];
+  __shared__ CmacItem items[kMaxItems];
+  __shared__ int s_wtot[2][2];  // [window parity][warp]: totals of the two scanning warps
   const int e = find_segment(prefix, n_ev, blockIdx.x);
   const EvDev& ev = evs[e];
   int local = blockIdx.x - __ldg(prefix + e);
@@ -412,191 +423,153 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
   local /= kBinCtas;
   const int ncg = (ev.C + kChanGroup - 1) / kChanGroup;
   const int cg = local % ncg;
-  const int run = local / ncg;
+  const int run0 = (local / ncg) * kCmacRuns;
   const int c0 = cg * kChanGroup;
   const int nc = min(kChanGroup, ev.C - c0);
-  const int b0 = run * kGm;
-  const int nb = min(kGm, ev.B_valid - b0);
   const int tid = threadIdx.x;
   const int bin = br * kCtaThreads + tid;
   const int K = ev.K, C = ev.C;
-  const long long kstride = (long long)C * kP;  // float2 elements between consecutive partitions of one IR
-  const int lmin = lrange[ev.blk0 + b0].x, lmax = lrange[ev.blk0 + b0 + nb - 1].y;
   const IrDev* __restrict__ irp = irs + ev.ir0;
   const float2* __restrict__ xbase = xspec + ev.xslot0 * kP + bin;
-  const float2* __restrict__ hbase = hspec + (ev.hslot0 + c0) * kP + bin;
-  float2* const ring_t = &ring[0][0][tid];  // this thread's column: stage stride 4*256, capsule stride 256 elements
+  const float2* const ring_t = &ring[0][0][tid];  // this thread's column: stage stride 4*256, capsule stride 256 elements
+  // H staging: 16-byte cp.async.cg copies (the north star's "coalesced float4 loads" of the spectra; L1 bypassed for data
+  // that is read once per CTA). The warp's 4 x 32-bin slice of an item is 64 pieces of 16 bytes, two per lane (capsule =
+  // piece / 16, bin pair = piece % 16), so a ring stage is warp-private: cp.async.wait_group + __syncwarp is the only
+  // synchronisation of the pipeline, no CTA barriers.
+  const int piece = (tid & ~31) + (tid & 15) * 2, pc = (tid >> 4) & 1;  // this lane's bin pair and its first capsule
+  const float2* const hsrc = hspec + (ev.hslot0 + c0 + pc) * kP + br * kCtaThreads + piece;
+  float2* const rdst = &ring[0][pc][piece];
+  const bool cp0 = pc < nc, cp1 = pc + 2 < nc;
 
-  float2 acc[kGm][kChanGroup];
+  // kCmacRuns consecutive runs per CTA, one after the other: an RIR whose outputs straddle a run boundary (40 % of the
+  // (RIR, partition) items with runs of 8 blocks) is read again by the next run. As separate CTAs the two reads are a CTA
+  // lifetime apart (~140 MB of other traffic: both miss L2, k_cmac read 1.4x its spectra from DRAM); in one CTA the second
+  // read follows the first within a few items and hits L2 (4.93 -> 4.73 ms per benchmark step).
+  int wpar = 0;
+  for (int run = run0; run < run0 + kCmacRuns && run * kGm < ev.B_valid; ++run) {
+    const int b0 = run * kGm;
+    const int nb = min(kGm, ev.B_valid - b0);
+    const int lmin = lrange[ev.blk0 + b0].x, lmax = lrange[ev.blk0 + b0 + nb - 1].y;
+    float2 acc[kGm][kChanGroup];
 #pragma unroll
-  for (int s = 0; s < kGm; ++s)
+    for (int s = 0; s < kGm; ++s)
 #pragma unroll
-    for (int c = 0; c < kChanGroup; ++c) acc[s][c] = make_float2(0.f, 0.f);
+      for (int c = 0; c < kChanGroup; ++c) acc[s][c] = make_float2(0.f, 0.f);
 
-  // Experiment (ALR_CMAC_ZIGZAG=1, off): odd runs walk their (IR, partition) items in DESCENDING order. Neighbouring runs
-  // share the items at the run boundary (each H partition contributes to 3-4 consecutive output blocks: 1.4x re-reads
-  // at a 10 % L2 hit rate); with alternating directions runs r and r+1 reach the shared items at the same end of their
-  // lists. Measured: k_cmac 5.80 -> 6.04 ms per benchmark step: CTAs of neighbouring runs do not stay in step, so the
-  // second read still misses L2, and the descending walk is slower on its own (profiles/r01_cmac_variants.txt).
-// H staging of k_cmac: 1 = 16-byte cp.async.cg copies, a warp owns its slice of a stage (the north star's "coalesced float4
-// loads" of the spectra; half the LDGSTS instructions, L1 bypassed for data that is read once per CTA); 0 = round 1's 8-byte
-// copies with thread-private stages. Measured equal within noise (k_cmac 4.98 vs 4.99 ms per benchmark step).
-#ifndef ALR_CMAC_COPY16
-#define ALR_CMAC_COPY16 1
-#endif
-#ifndef ALR_CMAC_ZIGZAG
-#define ALR_CMAC_ZIGZAG 0
-#endif
-  const int sgn = (ALR_CMAC_ZIGZAG && (run & 1)) ? -1 : 1;
-  const long long kstep = sgn * kstride;
-  const int n_win = (lmax - lmin + kMaxHeads) / kMaxHeads;
-  for (int wi = 0; wi < n_win; ++wi) {
-    const int l0 = lmin + kMaxHeads * (sgn > 0 ? wi : n_win - 1 - wi);
-    const int n_heads = min(kMaxHeads, lmax - l0 + 1);
-    __syncthreads();  // previous window fully consumed
-    if (tid < n_heads) {
-      const int l = l0 + tid;
-      const IrDev ir = irp[l];
-      CmacHead h;
-      h.d0 = b0 - ir.xb0;
-      h.xnb = ir.xnb;
-      h.k_lo = max(0, h.d0 - ir.xnb + 1);
-      h.k_hi = ir.xnb > 0 ? min(K - 1, h.d0 + nb - 1) : -1;
-      h.xoff = (long long)ir.xslot * kP;
-      h.hoff = ((long long)l * K + h.k_lo) * kstride;
-      heads[tid] = h;
-    }
-    __syncthreads();
-
-    // ---- producer state: next (IR, partition) item whose H values get copied into the ring
-    int ph = sgn > 0 ? -1 : n_heads, pk = 0, pk_left = 0;  // pk_left: partitions of the current IR still to produce
-    const float2* php = hbase;
-    bool prod_ok = true;
-    auto prod_advance = [&]() {
-      if (--pk_left > 0) {
-        pk += sgn;
-        php += kstep;
-        return;
+    for (int l0 = lmin; l0 <= lmax; l0 += kMaxHeads) {
+      // ---- the window's RIRs, one per thread: partitions k_lo..k_hi contribute to the run
+      const int n_heads = min(kMaxHeads, lmax - l0 + 1);
+      int k_lo = 0, cnt = 0, d0 = 0, xnb = 0, xslot = 0;
+      if (tid < n_heads) {
+        const IrDev ir = irp[l0 + tid];
+        d0 = b0 - ir.xb0;  // source block of output s and partition k: j = s + d0 - k, valid for 0 <= j < xnb
+        xnb = ir.xnb;
+        xslot = ir.xslot;
+        k_lo = max(0, d0 - xnb + 1);
+        cnt = xnb > 0 ? max(0, min(K - 1, d0 + nb - 1) - k_lo + 1) : 0;
       }
-      while ((unsigned)(ph += sgn) < (unsigned)n_heads) {
-        const CmacHead h = heads[ph];
-        if (h.k_lo <= h.k_hi) {
-          pk = sgn > 0 ? h.k_lo : h.k_hi;
-          pk_left = h.k_hi - h.k_lo + 1;
-          php = hbase + h.hoff + (long long)(pk - h.k_lo) * kstride;
-          // entering an IR: pull the source spectra it needs into L1 (kStages-1 items before they are used)
-          const int j_lo = max(0, h.d0 - h.k_hi), j_hi = min(h.xnb - 1, h.d0 + nb - 1 - h.k_lo);
-          const float2* xp = xbase + h.xoff;
-          for (int j = j_lo; j <= j_hi; ++j) prefetch_l1(xp + (long long)j * kP);
-          return;
+      int off = 0;  // exclusive prefix of cnt over the window's threads (warps 0 and 1)
+      if (tid < kMaxHeads) {
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, d);
+          if ((tid & 31) >= d) incl += v;
         }
+        off = incl - cnt;
+        if ((tid & 31) == 31) s_wtot[wpar][tid >> 5] = incl;
       }
-      prod_ok = false;
-    };
-    auto produce = [&](int stage) {
-      if (prod_ok) {
-#if ALR_CMAC_COPY16
-        // 16-byte copies ("float4 loads" of the spectra): the warp's 4 x 32-bin slice of an item is 64 pieces of 16 bytes, two
-        // per lane (capsule = piece / 16, bin pair = piece % 16); a stage is then warp-private instead of thread-private
-        float2* dst = &ring[stage][0][(tid & ~31) + (tid & 15) * 2];
-        const float2* src = php - tid + (tid & ~31) + (tid & 15) * 2;  // php points at this thread's own bin
-#pragma unroll
-        for (int q = 0; q < kChanGroup / 2; ++q) {
-          const int c = ((tid >> 4) & 1) + 2 * q;
-          if (c < nc) cp_async16(dst + c * kCtaThreads, src + c * kP);
-        }
-#else
-        float2* dst = ring_t + stage * (kChanGroup * kCtaThreads);
-#pragma unroll
-        for (int c = 0; c < kChanGroup; ++c)
-          if (c < nc) cp_async8(dst + c * kCtaThreads, php + c * kP);
-#endif
-        prod_advance();
-      }
-      cp_async_commit();  // (possibly empty) group: keeps the group count in step with the item count
-    };
-    // ---- consumer state
-    int ch = sgn > 0 ? -1 : n_heads, ck_left = 0, cjb = 0, cxnb = 0;
-    const float2* cxq = xbase;  // &X_l[jb][bin]: X of output s is cxq[s * kP]
-    bool cons_ok = true;
-    auto cons_advance = [&]() {
-      if (--ck_left > 0) {  // next partition k + sgn: source block j = s + d0 - k moves the other way
-        cjb -= sgn;
-        cxq -= sgn * kP;
-        return;
-      }
-      while ((unsigned)(ch += sgn) < (unsigned)n_heads) {
-        const CmacHead h = heads[ch];
-        if (h.k_lo <= h.k_hi) {
-          ck_left = h.k_hi - h.k_lo + 1;
-          cjb = h.d0 - (sgn > 0 ? h.k_lo : h.k_hi);
-          cxnb = h.xnb;
-          cxq = xbase + h.xoff + (long long)cjb * kP;
-          return;
-        }
-      }
-      cons_ok = false;
-    };
-    prod_advance();
-    cons_advance();
-#pragma unroll
-    for (int i = 0; i < kStages - 1; ++i) produce(i);
-    int stage = 0;
-    while (cons_ok) {
-#if ALR_CMAC_COPY16
-      cp_async_wait<kStages - 2>();  // this lane's pieces of the consumer's item have landed ...
-      __syncwarp();                  // ... and the other lanes'; every lane is done with the previous stage
-      const float2* src = ring_t + stage * (kChanGroup * kCtaThreads);
-      float2 h[kChanGroup];
-#pragma unroll
-      for (int c = 0; c < kChanGroup; ++c) h[c] = (c < nc) ? src[c * kCtaThreads] : make_float2(0.f, 0.f);
-      produce(stage == 0 ? kStages - 1 : stage - 1);  // refill the slot consumed in the previous iteration
-#else
-      produce(stage == 0 ? kStages - 1 : stage - 1);  // refill the slot consumed in the previous iteration
-      cp_async_wait<kStages - 1>();                    // the consumer's item has landed
-      const float2* src = ring_t + stage * (kChanGroup * kCtaThreads);
-      float2 h[kChanGroup];
-#pragma unroll
-      for (int c = 0; c < kChanGroup; ++c) h[c] = (c < nc) ? src[c * kCtaThreads] : make_float2(0.f, 0.f);
-#endif
-      // outputs s with 0 <= s + jb < xnb and s < nb
-      const int s_lo = max(0, -cjb);
-      const unsigned s_cnt = (unsigned)max(0, min(nb, cxnb - cjb) - s_lo);
-      // The validity test is warp-uniform. ptxas if-converts a single 16-FFMA body into predicated code, which
-      // still costs an issue slot per predicated-off FFMA (45 % of them for moving events, profiles/r01d_cmac.txt),
-      // so the bodies are PAIRS of output blocks (32 FFMA): large enough to stay real basic blocks behind a
-      // uniform branch. A block of a pair that is itself out of range gets a zero source value.
-#pragma unroll
-      for (int s = 0; s < kGm; s += 2) {
-        const bool v0 = (unsigned)(s - s_lo) < s_cnt, v1 = (unsigned)(s + 1 - s_lo) < s_cnt;
-        if (v0 || v1) {
-          float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
-          if (v0) x0 = __ldg(cxq + s * kP);
-          if (v1) x1 = __ldg(cxq + (s + 1) * kP);
-#pragma unroll
-          for (int c = 0; c < kChanGroup; ++c) {
-            acc[s][c].x = fmaf(x0.x, h[c].x, acc[s][c].x);
-            acc[s][c].x = fmaf(-x0.y, h[c].y, acc[s][c].x);
-            acc[s][c].y = fmaf(x0.x, h[c].y, acc[s][c].y);
-            acc[s][c].y = fmaf(x0.y, h[c].x, acc[s][c].y);
-            acc[s + 1][c].x = fmaf(x1.x, h[c].x, acc[s + 1][c].x);
-            acc[s + 1][c].x = fmaf(-x1.y, h[c].y, acc[s + 1][c].x);
-            acc[s + 1][c].y = fmaf(x1.x, h[c].y, acc[s + 1][c].y);
-            acc[s + 1][c].y = fmaf(x1.y, h[c].x, acc[s + 1][c].y);
+      __syncthreads();  // s_wtot written; the previous window's list is consumed
+      const int total = s_wtot[wpar][0] + s_wtot[wpar][1];
+      if (tid >= 32) off += s_wtot[wpar][0];
+      wpar ^= 1;  // the next window's totals go to the other pair: a thread may still be reading these
+      for (int pass = 0; pass < total; pass += kMaxItems) {
+        if (pass > 0) __syncthreads();  // previous pass consumed
+        if (cnt > 0) {
+          const int i1 = min(off + cnt, pass + kMaxItems);
+          for (int i = max(off, pass); i < i1; ++i) {
+            const int k = k_lo + (i - off), jb = d0 - k;
+            const int s_lo = max(0, -jb), s_hi = min(nb, xnb - jb);
+            CmacItem it;
+            it.hrow = ((l0 + tid) * K + k) * C;
+            it.xrow = xslot + jb;
+            it.mask = ((1 << s_hi) - 1) & ~((1 << s_lo) - 1);
+            it.pfrow = it.xrow + s_lo;
+            if (k == k_lo) it.mask |= (it.mask & (it.mask - 1)) << 8;  // entering the RIR: every other row is new as well
+            items[i - pass] = it;
           }
         }
+        __syncthreads();
+        const int n_items = min(kMaxItems, total - pass);
+
+        // ---- pipeline: the producer side runs kStages-1 items ahead of the consumer side in the same thread
+        auto produce = [&](int i, int stage) {
+          if (i < n_items) {
+#if ALR_CMAC_PF
+            const CmacItem it = items[i];
+            const float2* src = hsrc + (long long)it.hrow * kP;
+#else
+            const float2* src = hsrc + (long long)items[i].hrow * kP;
+#endif
+            float2* dst = rdst + stage * (kChanGroup * kCtaThreads);
+            if (cp0) cp_async16(dst, src);
+            if (cp1) cp_async16(dst + 2 * kCtaThreads, src + 2 * kP);
+#if ALR_CMAC_PF
+            // the source spectra the item reads for the first time go to L1 now, kStages-1 items before they are used
+            prefetch_l1(xbase + (long long)it.pfrow * kP);
+            for (int m = it.mask >> 8; m; m &= m - 1) prefetch_l1(xbase + (long long)(it.xrow + __ffs(m) - 1) * kP);
+#endif
+          }
+          cp_async_commit();  // (possibly empty) group: keeps the group count in step with the item count
+        };
+#pragma unroll
+        for (int i = 0; i < kStages - 1; ++i) produce(i, i);
+        int stage = 0;
+        for (int i = 0; i < n_items; ++i) {
+          cp_async_wait<kStages - 2>();  // this lane's pieces of item i have landed ...
+          __syncwarp();                  // ... and the other lanes'; every lane is done with the previous stage
+          const float2* src = ring_t + stage * (kChanGroup * kCtaThreads);
+          float2 h[kChanGroup];
+#pragma unroll
+          for (int c = 0; c < kChanGroup; ++c) h[c] = (c < nc) ? src[c * kCtaThreads] : make_float2(0.f, 0.f);
+          produce(i + kStages - 1, stage == 0 ? kStages - 1 : stage - 1);  // refill the slot consumed one iteration ago
+          const CmacItem it = items[i];
+          const float2* cxq = xbase + (long long)it.xrow * kP;  // X of output s is cxq[s * kP]
+          // The validity test is warp-uniform. ptxas if-converts a single 16-FFMA body into predicated code, which
+          // still costs an issue slot per predicated-off FFMA (45 % of them for moving events, profiles/r01d_cmac.txt),
+          // so the bodies are PAIRS of output blocks (32 FFMA): large enough to stay real basic blocks behind a
+          // uniform branch. A block of a pair that is itself out of range gets a zero source value.
+#pragma unroll
+          for (int s = 0; s < kGm; s += 2) {
+            if (it.mask & (3 << s)) {
+              float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
+              if (it.mask & (1 << s)) x0 = __ldg(cxq + s * kP);
+              if (it.mask & (2 << s)) x1 = __ldg(cxq + (s + 1) * kP);
+#pragma unroll
+              for (int c = 0; c < kChanGroup; ++c) {
+                acc[s][c].x = fmaf(x0.x, h[c].x, acc[s][c].x);
+                acc[s][c].x = fmaf(-x0.y, h[c].y, acc[s][c].x);
+                acc[s][c].y = fmaf(x0.x, h[c].y, acc[s][c].y);
+                acc[s][c].y = fmaf(x0.y, h[c].x, acc[s][c].y);
+                acc[s + 1][c].x = fmaf(x1.x, h[c].x, acc[s + 1][c].x);
+                acc[s + 1][c].x = fmaf(-x1.y, h[c].y, acc[s + 1][c].x);
+                acc[s + 1][c].y = fmaf(x1.x, h[c].y, acc[s + 1][c].y);
+                acc[s + 1][c].y = fmaf(x1.y, h[c].x, acc[s + 1][c].y);
+              }
+            }
+          }
+          stage = (stage + 1 == kStages) ? 0 : stage + 1;
+        }
+        cp_async_wait<0>();
       }
-      cons_advance();
-      stage = (stage + 1 == kStages) ? 0 : stage + 1;
     }
-    cp_async_wait<0>();
-  }
 #pragma unroll
-  for (int s = 0; s < kGm; ++s)
-    if (s < nb)
+    for (int s = 0; s < kGm; ++s)
+      if (s < nb)
 #pragma unroll
-      for (int c = 0; c < kChanGroup; ++c)
-        if (c < nc) ALR_SPEC_STORE(yspec + (ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin, acc[s][c]);
+        for (int c = 0; c < kChanGroup; ++c)
+          if (c < nc) ALR_SPEC_STORE(yspec + (ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin, acc[s][c]);
+  }  // run
 }
 
 // k_cmac_static: the same contraction for STATIC events (one IR, every source block active), where it is a plain

@@ -259,9 +259,9 @@ int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0,
     }
   }
   const int ncg = (C + kChanGroup - 1) / kChanGroup;
-  const long long n_cmac = (long long)ceil_div(z.B_valid, kGm) * ncg * kBinCtas;
+  const long long n_cmac = (long long)ceil_div(ceil_div(z.B_valid, kGm), kCmacRuns) * ncg * kBinCtas;
   const long long n_ifft = (long long)((C + kIfftCh - 1) / kIfftCh) * ceil_div(z.B_out, kRun);
-  if (z.h > 0x3ffffff0LL || n_cmac > 0x3ffffff0LL || z.xb > 0x3ffffff0LL)
+  if (z.h > 0x3ffffff0LL || n_cmac * kCmacRuns > 0x3ffffff0LL || z.xb > 0x3ffffff0LL)
     return fail(ALR_ERR_INVALID, "event %d: too large for 32-bit task indices", idx);
   // small_mode: 0 off, 1 caller's event, 2 dry / direct-path sub-event (its RIR is the window of at most
   // dry_low + dry_high taps that k_dry_window selects)
@@ -288,7 +288,7 @@ int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0,
   }
   if (z.fused) {
     z.n_ptask = N * C * (z.fused == 2 ? kSwKSplit : 1);
-    z.n_ctask = z.fused == 1 ? (int)n_cmac : 0;
+    z.n_ctask = z.fused == 1 ? ceil_div(z.B_valid, kGm) * ncg * kBinCtas : 0;  // k_mov_fused: one C-task per run
     z.h_ws = 0;
     z.n_irfft = 0;
     z.n_cmac = 0;
