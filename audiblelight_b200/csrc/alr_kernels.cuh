@@ -146,15 +146,28 @@ __device__ __forceinline__ float warp_max(float v) {
 // already under way in other warps; a single-buffered version of that mixed the energies of neighbouring tasks
 // about every second run of a 40-event batch (racecheck blind), and the double-buffered fix was never explained.
 // There is no shared reduction state any more: nothing is read that another warp may be rewriting.
+// ALR_IRFFT_NT=2 (experiment, off): two partitions per pass through the transform share every derived twiddle (a third
+// of the transform's floating-point instructions), but need 128 registers and 70 KB of shared memory, i.e. 2 CTAs per SM
+// instead of 4: k_ir_fft 6.35 -> 8.40 ms per benchmark step (profiles/r02_micro_variants.txt). Latency hiding by
+// occupancy is worth more here than the saved arithmetic.
+#ifndef ALR_IRFFT_NT
+#define ALR_IRFFT_NT 1
+#endif
 #ifndef ALR_IRFFT_MINB  // occupancy experiment, profiles/r01_irfft_occupancy.txt: 4 CTAs per SM (64 registers) is fastest
 #define ALR_IRFFT_MINB 4
 #endif
 constexpr int kEnWarps = kGroup / 32;  // energy partials per spectrum slot
+constexpr size_t kIrFftSmem = ALR_IRFFT_NT == 2 ? sizeof(FftSmem) * 2 * kGroupsPerCta : 0;  // dynamic part
 __global__ void __launch_bounds__(kCtaThreads, ALR_IRFFT_MINB)
 k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, int n_tasks,
          const float2* __restrict__ tw, const float2* __restrict__ zeta, float2* __restrict__ hspec,
          float* __restrict__ hen) {
+#if ALR_IRFFT_NT == 2
+  extern __shared__ __align__(16) unsigned char ir_dyn[];  // 2 x FftSmem per group: beyond the 48 KB static limit at P = 4096
+  FftSmem (*sm)[2] = reinterpret_cast<FftSmem (*)[2]>(ir_dyn);
+#else
   __shared__ FftSmem sm[kGroupsPerCta];
+#endif
   const int g = threadIdx.x / kGroup, t = threadIdx.x % kGroup, bar = 1 + g;
   // Each group transforms kIrTasks consecutive partitions: the event lookup (a chain of ~8 dependent loads) and the
   // descriptor reads are paid once per group instead of once per transform (consecutive tasks share the event).
@@ -165,9 +178,8 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
   const float2 zt = __ldg(zeta + t);
   int c = 0, k = 0, l = 0;
   bool fresh = true;  // (c, k, l) must be derived from the task index: first task of the group or a new event
-  for (int i = 0; i < kIrTasks; ++i) {
-    const int task = task0 + i;
-    if (task >= n_tasks) break;
+  // one task: event / partition bookkeeping, the 16 taps of this thread, the warp's energy partial; returns the slot
+  auto load_task = [&](int task, float (&a)[16]) -> long long {
     while (task >= seg_hi) {  // next event (empty segments are skipped)
       ++e;
       seg_lo = seg_hi;
@@ -192,7 +204,6 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
     const float* __restrict__ src = ev.irs + (long long)c * ev.ir_stride_c + (long long)l * ev.ir_stride_n;
     const int t0 = k * kP;
     const int lo = max(ev.mask_lo, t0), hi = min(min(ev.mask_hi, ev.Lh), t0 + kP);
-    float a[16];
     float en = 0.f;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
@@ -203,8 +214,35 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
     const long long slot = ev.hslot0 + (long long)(l * ev.K + k) * ev.C + c;
     en = warp_sum(en);
     if ((t & 31) == 0) hen[slot * kEnWarps + (t >> 5)] = en;
+    return slot;
+  };
+#if ALR_IRFFT_NT == 2
+  // two partitions per pass through the transform: they share every derived twiddle (a third of the transform's
+  // floating-point instructions) and the group barriers
+  for (int i = 0; i < kIrTasks; i += 2) {
+    const int task = task0 + i;
+    if (task >= n_tasks) break;
+    float a[2][16];
+    float2* spec[2];
+    spec[0] = hspec + load_task(task, a[0]) * kP;
+    if (i + 1 < kIrTasks && task + 1 < n_tasks) {
+      spec[1] = hspec + load_task(task + 1, a[1]) * kP;
+    } else {
+      spec[1] = nullptr;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) a[1][r] = 0.f;
+    }
+    fwd_blocks_to_global<2>(a, zt, sm[g], tw, t, bar, spec);  // contains group barriers, ends with one
+  }
+#else
+  for (int i = 0; i < kIrTasks; ++i) {
+    const int task = task0 + i;
+    if (task >= n_tasks) break;
+    float a[16];
+    const long long slot = load_task(task, a);
     fwd_block_to_global(a, zt, sm[g], tw, t, bar, hspec + slot * kP);  // contains group barriers, ends with one
   }
+#endif
 }
 
 // k_ir_scale: a_l = 1 / mean_c( sqrt(sum_t h_{l,c}^2) + tiny )  (normalize_irs on the (N, C, Lh) view), times 512

@@ -801,6 +801,12 @@ int alr_create(int device, alr_context** out) {
     delete ctx;
     return rc;
   }
+  if (kIrFftSmem > 0 &&
+      cudaFuncSetAttribute(k_ir_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIrFftSmem) != cudaSuccess) {
+    cudaGetLastError();
+    delete ctx;
+    return fail(ALR_ERR_CUDA, "k_ir_fft: cannot reserve %zu bytes of shared memory", kIrFftSmem);
+  }
   {
     // k_mov_fused is a persistent launch: exactly as many CTAs as can be resident at once
     int sms = 0, per_sm = 0, khz = 0;
@@ -1820,7 +1826,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         LAUNCH_CHECK(kCatIfft);
       }
       if (n_irfft > 0) {
-        k_ir_fft<<<ceil_div(n_irfft, kGroupsPerCta * kIrTasks), kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_irfft),
+        k_ir_fft<<<ceil_div(n_irfft, kGroupsPerCta * kIrTasks), kCtaThreads, kIrFftSmem, st>>>(c_evs, ne, (const int*)(db + ch.off_irfft),
                                                                         n_irfft, ctx->d_tw, ctx->d_zeta, d_hspec, d_hen);
         LAUNCH_CHECK(kCatIrFft);
         k_ir_scale<<<ceil_div((long long)n_irs * 32, 128), 128, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_ir), n_irs,
