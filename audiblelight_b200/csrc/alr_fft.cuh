@@ -316,7 +316,7 @@ __device__ __forceinline__ float2 zeta_step(int r) {
 // Forward: the caller passes the real samples a[t + kGroup r] in a[r] (second half implicitly zero); zt = zeta^t.
 __device__ __forceinline__ void fwd_block_to_global(const float (&a)[16], float2 zt, FftSmem& s,
                                                     const float2* __restrict__ tw, int t, int bar,
-                                                    float2* __restrict__ spec) {
+                                                    float2* __restrict__ spec, int stride256 = 256) {
   float2 v[16];
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
@@ -328,7 +328,7 @@ __device__ __forceinline__ void fwd_block_to_global(const float (&a)[16], float2
 #pragma unroll
   for (int m = 0; m < kM3; ++m)
 #pragma unroll
-    for (int k = 0; k < kR3; ++k) ALR_SPEC_STORE(spec + t + kGroup * m + 256 * k, o[m][k]);
+    for (int k = 0; k < kR3; ++k) ALR_SPEC_STORE(spec + t + kGroup * m + stride256 * k, o[m][k]);  // stride256: distance of the 256-bin tiles
   group_sync(bar);  // pass-C gathers done before the next transform's scatter
 }
 
@@ -336,7 +336,7 @@ __device__ __forceinline__ void fwd_block_to_global(const float (&a)[16], float2
 template <int NT>
 __device__ __forceinline__ void fwd_blocks_to_global(const float (&a)[NT][16], float2 zt, FftSmem* __restrict__ s,
                                                      const float2* __restrict__ tw, int t, int bar,
-                                                     float2* (&spec)[NT]) {
+                                                     float2* (&spec)[NT], int stride256 = 256) {
   float2 v[NT][16];
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
@@ -352,7 +352,7 @@ __device__ __forceinline__ void fwd_blocks_to_global(const float (&a)[NT][16], f
 #pragma unroll
       for (int m = 0; m < kM3; ++m)
 #pragma unroll
-        for (int k = 0; k < kR3; ++k) __stcg(spec[q] + t + kGroup * m + 256 * k, o[q][m][k]);
+        for (int k = 0; k < kR3; ++k) __stcg(spec[q] + t + kGroup * m + stride256 * k, o[q][m][k]);
     }
   group_sync(bar);  // pass-C gathers done before the next transform's scatter
 }

@@ -150,6 +150,12 @@ __device__ __forceinline__ float warp_max(float v) {
 // of the transform's floating-point instructions), but need 128 registers and 70 KB of shared memory, i.e. 2 CTAs per SM
 // instead of 4: k_ir_fft 6.35 -> 8.40 ms per benchmark step (profiles/r02_micro_variants.txt). Latency hiding by
 // occupancy is worth more here than the saved arithmetic.
+// ALR_H_TILED: layout of the RIR spectra of one (RIR, partition): 0 = [capsule][P bins]; 1 = [256-bin tile][capsule][256 bins],
+// so that the 4 capsules x 256 bins a multiply-accumulate CTA reads per item are one contiguous 8 KB piece instead of four
+// 2 KB pieces 32 KB apart.
+#ifndef ALR_H_TILED
+#define ALR_H_TILED 0
+#endif
 #ifndef ALR_IRFFT_NT
 #define ALR_IRFFT_NT 1
 #endif
@@ -179,7 +185,8 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
   int c = 0, k = 0, l = 0;
   bool fresh = true;  // (c, k, l) must be derived from the task index: first task of the group or a new event
   // one task: event / partition bookkeeping, the 16 taps of this thread, the warp's energy partial; returns the slot
-  auto load_task = [&](int task, float (&a)[16]) -> long long {
+  int stride256 = 256;
+  auto load_task = [&](int task, float (&a)[16]) -> float2* {
     while (task >= seg_hi) {  // next event (empty segments are skipped)
       ++e;
       seg_lo = seg_hi;
@@ -214,7 +221,12 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
     const long long slot = ev.hslot0 + (long long)(l * ev.K + k) * ev.C + c;
     en = warp_sum(en);
     if ((t & 31) == 0) hen[slot * kEnWarps + (t >> 5)] = en;
-    return slot;
+#if ALR_H_TILED
+    stride256 = ev.C * 256;
+    return hspec + (ev.hslot0 + (long long)(l * ev.K + k) * ev.C) * kP + c * 256;
+#else
+    return hspec + slot * kP;
+#endif
   };
 #if ALR_IRFFT_NT == 2
   // two partitions per pass through the transform: they share every derived twiddle (a third of the transform's
@@ -224,23 +236,23 @@ k_ir_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix
     if (task >= n_tasks) break;
     float a[2][16];
     float2* spec[2];
-    spec[0] = hspec + load_task(task, a[0]) * kP;
+    spec[0] = load_task(task, a[0]);
     if (i + 1 < kIrTasks && task + 1 < n_tasks) {
-      spec[1] = hspec + load_task(task + 1, a[1]) * kP;
+      spec[1] = load_task(task + 1, a[1]);  // (stride256 of the second task: same event assumed, see below)
     } else {
       spec[1] = nullptr;
 #pragma unroll
       for (int r = 0; r < 16; ++r) a[1][r] = 0.f;
     }
-    fwd_blocks_to_global<2>(a, zt, sm[g], tw, t, bar, spec);  // contains group barriers, ends with one
+    fwd_blocks_to_global<2>(a, zt, sm[g], tw, t, bar, spec, stride256);  // contains group barriers, ends with one
   }
 #else
   for (int i = 0; i < kIrTasks; ++i) {
     const int task = task0 + i;
     if (task >= n_tasks) break;
     float a[16];
-    const long long slot = load_task(task, a);
-    fwd_block_to_global(a, zt, sm[g], tw, t, bar, hspec + slot * kP);  // contains group barriers, ends with one
+    float2* spec = load_task(task, a);
+    fwd_block_to_global(a, zt, sm[g], tw, t, bar, spec, stride256);  // contains group barriers, ends with one
   }
 #endif
 }
@@ -387,6 +399,9 @@ constexpr int kG = 8;       // output blocks per CTA (k_cmac_static)
 #define ALR_CMAC_STAGES 5
 #endif
 constexpr int kGm = ALR_CMAC_G;            // output blocks per CTA (k_cmac); even
+#ifndef ALR_CMAC_ORDER
+#define ALR_CMAC_ORDER 0
+#endif
 #ifndef ALR_CMAC_RUNS
 #define ALR_CMAC_RUNS 4
 #endif
@@ -447,21 +462,41 @@ constexpr int kMaxItems = 448;  // list capacity (7 KB); longer windows are work
 #define ALR_CMAC_PF 1
 #endif
 
-__global__ void __launch_bounds__(kCtaThreads, 2)
-k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const IrDev* __restrict__ irs,
-       const int2* __restrict__ lrange, const float2* __restrict__ xspec, const float2* __restrict__ hspec,
-       float2* __restrict__ yspec) {
-  __shared__ float2 ring[kStages][kChanGroup][kCtaThreads];
-  __shared__ CmacItem items[kMaxItems];
-  __shared__ int s_wtot[2][2];  // [window parity][warp]: totals of the two scanning warps
-  const int e = find_segment(prefix, n_ev, blockIdx.x);
+struct CmacSmem {
+  float2 ring[kStages][kChanGroup][kCtaThreads];
+  CmacItem items[kMaxItems];
+  int wtot[2][2];  // [window parity][warp]: totals of the two scanning warps
+};
+constexpr size_t kCmacSmem = sizeof(CmacSmem);  // dynamic shared memory of k_cmac / k_cmac_both (beyond 48 KB with deeper rings)
+
+// `vb` is the CTA's index among the mover CTAs (blockIdx.x for k_cmac, the de-interleaved index for k_cmac_both)
+__device__ __forceinline__ void cmac_mover_cta(CmacSmem& sh, int vb, const EvDev* __restrict__ evs, int n_ev,
+                                               const int* __restrict__ prefix, const IrDev* __restrict__ irs,
+                                               const int2* __restrict__ lrange, const float2* __restrict__ xspec,
+                                               const float2* __restrict__ hspec, float2* __restrict__ yspec) {
+  float2 (&ring)[kStages][kChanGroup][kCtaThreads] = sh.ring;
+  CmacItem (&items)[kMaxItems] = sh.items;
+  int (&s_wtot)[2][2] = sh.wtot;
+  const int e = find_segment(prefix, n_ev, vb);
   const EvDev& ev = evs[e];
-  int local = blockIdx.x - __ldg(prefix + e);
+  int local = vb - __ldg(prefix + e);
+  const int ncg = (ev.C + kChanGroup - 1) / kChanGroup;
+#if ALR_CMAC_ORDER == 1
+  // Experiment (off): CTA order [256-bin tile][run group][capsule group], so that CTAs starting within microseconds of each
+  // other share what they read (capsule groups of a run: the source spectra; neighbouring runs: the RIRs straddling them).
+  // No gain (4.26-4.29 ms at 2-4 runs per CTA, 4.53 at 1): with the default order k_cmac already reads only 1.11x its
+  // unique bytes from DRAM (20.8 GB per step for 16.7 GB of RIR spectra + 2 GB of source spectra) at 5.3 TB/s.
+  const int nrg = ((ev.B_valid + kGm - 1) / kGm + kCmacRuns - 1) / kCmacRuns;
+  const int cg = local % ncg;
+  local /= ncg;
+  const int run0 = (local % nrg) * kCmacRuns;
+  const int br = local / nrg;
+#else
   const int br = local % kBinCtas;
   local /= kBinCtas;
-  const int ncg = (ev.C + kChanGroup - 1) / kChanGroup;
   const int cg = local % ncg;
   const int run0 = (local / ncg) * kCmacRuns;
+#endif
   const int c0 = cg * kChanGroup;
   const int nc = min(kChanGroup, ev.C - c0);
   const int tid = threadIdx.x;
@@ -475,7 +510,13 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
   // piece / 16, bin pair = piece % 16), so a ring stage is warp-private: cp.async.wait_group + __syncwarp is the only
   // synchronisation of the pipeline, no CTA barriers.
   const int piece = (tid & ~31) + (tid & 15) * 2, pc = (tid >> 4) & 1;  // this lane's bin pair and its first capsule
+#if ALR_H_TILED
+  const float2* const hsrc = hspec + ev.hslot0 * kP + (long long)br * (ev.C * 256) + (c0 + pc) * 256 + piece;
+  constexpr int kCapStride = 256;  // capsules of one 256-bin tile are adjacent: an item is ONE contiguous 8 KB read
+#else
   const float2* const hsrc = hspec + (ev.hslot0 + c0 + pc) * kP + br * kCtaThreads + piece;
+  constexpr int kCapStride = kP;
+#endif
   float2* const rdst = &ring[0][pc][piece];
   const bool cp0 = pc < nc, cp1 = pc + 2 < nc;
 
@@ -551,7 +592,7 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
 #endif
             float2* dst = rdst + stage * (kChanGroup * kCtaThreads);
             if (cp0) cp_async16(dst, src);
-            if (cp1) cp_async16(dst + 2 * kCtaThreads, src + 2 * kP);
+            if (cp1) cp_async16(dst + 2 * kCtaThreads, src + 2 * kCapStride);
 #if ALR_CMAC_PF
             // the source spectra the item reads for the first time go to L1 now, kStages-1 items before they are used
             prefetch_l1(xbase + (long long)it.pfrow * kP);
@@ -610,6 +651,15 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
   }  // run
 }
 
+__global__ void __launch_bounds__(kCtaThreads, 2)
+k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const IrDev* __restrict__ irs,
+       const int2* __restrict__ lrange, const float2* __restrict__ xspec, const float2* __restrict__ hspec,
+       float2* __restrict__ yspec) {
+  extern __shared__ __align__(16) unsigned char cmac_dyn[];
+  CmacSmem& sh = *reinterpret_cast<CmacSmem*>(cmac_dyn);
+  cmac_mover_cta(sh, blockIdx.x, evs, n_ev, prefix, irs, lrange, xspec, hspec, yspec);
+}
+
 // k_cmac_static: the same contraction for STATIC events (one IR, every source block active), where it is a plain
 // block-FIR  Y[b,c] = sum_k X[b-k] * H[k,c]  and completely regular: all kG outputs of the run are live in every
 // partition step, so there are no per-IR headers, iterators or validity branches. Static events are 40 % of the
@@ -631,12 +681,13 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
 #define ALR_STATIC_OCC 2
 #endif
 constexpr int kStaticCh = ALR_STATIC_CH;  // capsules per thread in k_cmac_static
-__global__ void __launch_bounds__(kCtaThreads, ALR_STATIC_OCC)
-k_cmac_static(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const IrDev* __restrict__ irs,
-              const float2* __restrict__ xspec, const float2* __restrict__ hspec, float2* __restrict__ yspec) {
-  const int e = find_segment(prefix, n_ev, blockIdx.x);
+__device__ __forceinline__ void cmac_static_cta(int vb, const EvDev* __restrict__ evs, int n_ev,
+                                                const int* __restrict__ prefix, const IrDev* __restrict__ irs,
+                                                const float2* __restrict__ xspec, const float2* __restrict__ hspec,
+                                                float2* __restrict__ yspec) {
+  const int e = find_segment(prefix, n_ev, vb);
   const EvDev& ev = evs[e];
-  int local = blockIdx.x - __ldg(prefix + e);
+  int local = vb - __ldg(prefix + e);
   const int br = local % kBinCtas;
   local /= kBinCtas;
   const int ncg = (ev.C + kStaticCh - 1) / kStaticCh;
@@ -651,13 +702,19 @@ k_cmac_static(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ p
   const int xnb = irs[ev.ir0].xnb;
   const long long kstride = (long long)C * kP;
   const float2* __restrict__ xbase = xspec + ev.xslot0 * kP + bin;
+#if ALR_H_TILED
+  const float2* __restrict__ hbase = hspec + ev.hslot0 * kP + (long long)br * (ev.C * 256) + c0 * 256 + threadIdx.x;
+  constexpr int kCapStride = 256;
+#else
   const float2* __restrict__ hbase = hspec + (ev.hslot0 + c0) * kP + bin;
+  constexpr int kCapStride = kP;
+#endif
   const float2 zero = make_float2(0.f, 0.f);
   auto load_x = [&](int j) -> float2 { return (j >= 0 && j < xnb) ? __ldg(xbase + (long long)j * kP) : zero; };
   auto load_h = [&](int k, float2 (&h)[kStaticCh]) {
     if (k < K) {
 #pragma unroll
-      for (int c = 0; c < kStaticCh; ++c) h[c] = (c < nc) ? __ldg(hbase + k * kstride + (long long)c * kP) : zero;
+      for (int c = 0; c < kStaticCh; ++c) h[c] = (c < nc) ? __ldg(hbase + k * kstride + (long long)c * kCapStride) : zero;
     }
   };
 #if ALR_FFMA2
@@ -744,6 +801,31 @@ k_cmac_static(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ p
 #else
         if (c < nc) ALR_SPEC_STORE(yspec + (ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin, acc[s][c]);
 #endif
+}
+
+__global__ void __launch_bounds__(kCtaThreads, ALR_STATIC_OCC)
+k_cmac_static(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, const IrDev* __restrict__ irs,
+              const float2* __restrict__ xspec, const float2* __restrict__ hspec, float2* __restrict__ yspec) {
+  cmac_static_cta(blockIdx.x, evs, n_ev, prefix, irs, xspec, hspec, yspec);
+}
+
+// k_cmac_both: the CTAs of k_cmac and k_cmac_static in ONE grid, interleaved at their ratio. Launched one after the other
+// the two kernels leave complementary halves of the SM idle: k_cmac streams spectra (DRAM- and L2-bound pipeline), a
+// k_cmac_static CTA is 6 short steps behind a long chain of dependent loads (48 % long-scoreboard stalls, 38 % of the DRAM
+// bandwidth). Both are 2 CTAs per SM at 128 registers, so a mixed grid makes the typical SM hold one of each.
+// Every `period`-th CTA is a static one until the n_static are used up: CTA b is static iff (b + 1) % period == 0 and
+// (b + 1) / period <= n_static.
+__global__ void __launch_bounds__(kCtaThreads, 2)
+k_cmac_both(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix_m, const int* __restrict__ prefix_s,
+            int n_static, int period, const IrDev* __restrict__ irs, const int2* __restrict__ lrange,
+            const float2* __restrict__ xspec, const float2* __restrict__ hspec, float2* __restrict__ yspec) {
+  extern __shared__ __align__(16) unsigned char cmac_dyn[];
+  CmacSmem& sh = *reinterpret_cast<CmacSmem*>(cmac_dyn);
+  const int q = (blockIdx.x + 1) / period;
+  if (q * period == blockIdx.x + 1 && q <= n_static)
+    cmac_static_cta(q - 1, evs, n_ev, prefix_s, irs, xspec, hspec, yspec);
+  else
+    cmac_mover_cta(sh, blockIdx.x - min(q, n_static), evs, n_ev, prefix_m, irs, lrange, xspec, hspec, yspec);
 }
 
 // k_ifft_ola: one CTA per (event, group of 4 capsules, run of kRun output blocks); group g handles capsule c0+g.

@@ -110,6 +110,7 @@ struct alr_context {
   int fused_grid = 0;                     // resident CTAs of k_mov_fused (SMs x occupancy)
   int sm_clock_khz = 0;
   int mix_group = 0;                      // scenes per ambience-reduction + mixdown group (0: all at once)
+  int cmac_merge = 0;                     // k_cmac and k_cmac_static CTAs interleaved in one grid (k_cmac_both)
   long long watchdog_ms = 2000;           // ALR_WATCHDOG_MS: how long a persistent kernel may wait for one dependency
   int small_rir = 1;                      // k_small_rir for RIRs of at most one partition (ALR_SMALL=0: general pipeline)
   int64_t l2_persist_bytes = 0;           // L2 set aside for persisting lines (the ring of k_mov_sweep); 0: off
@@ -294,7 +295,8 @@ int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0,
     z.n_cmac = 0;
   }
   const long long n_cmac_s = (long long)ceil_div(z.B_valid, kG) * ((C + kStaticCh - 1) / kStaticCh) * kBinCtas;
-  z.n_cmac_static = moving ? 0 : (int)n_cmac_s;  // regular block-FIR kernel: static events
+  z.n_cmac_static = moving ? 0 : (int)n_cmac_s;  // regular block-FIR kernel: static events (through k_cmac's item list they
+                                                 // take the same time: 5.78 vs 4.26 + 1.58 ms, profiles/r02_micro_variants.txt)
   z.n_ifft = (int)n_ifft;
   z.n_parts = (int)n_ifft;
   return ALR_OK;
@@ -801,6 +803,12 @@ int alr_create(int device, alr_context** out) {
     delete ctx;
     return rc;
   }
+  if (cudaFuncSetAttribute(k_cmac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmacSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(k_cmac_both, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmacSmem) != cudaSuccess) {
+    cudaGetLastError();
+    delete ctx;
+    return fail(ALR_ERR_CUDA, "k_cmac: cannot reserve %zu bytes of shared memory", kCmacSmem);
+  }
   if (kIrFftSmem > 0 &&
       cudaFuncSetAttribute(k_ir_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIrFftSmem) != cudaSuccess) {
     cudaGetLastError();
@@ -854,6 +862,7 @@ int alr_create(int device, alr_context** out) {
     if (const char* v = getenv("ALR_RING_MB")) ctx->ring_bytes = std::max<int64_t>(1, atoll(v)) << 20;
     if (const char* v = getenv("ALR_LOOKAHEAD")) ctx->lookahead = std::max(0, atoi(v));
     if (const char* v = getenv("ALR_MIX_GROUP")) ctx->mix_group = std::max(0, atoi(v));
+    if (const char* v = getenv("ALR_CMAC_MERGE")) ctx->cmac_merge = atoi(v) != 0;
     if (const char* v = getenv("ALR_SMALL")) ctx->small_rir = atoi(v) != 0;
     if (const char* v = getenv("ALR_WATCHDOG_MS")) ctx->watchdog_ms = std::max(1LL, atoll(v));
   }
@@ -911,6 +920,8 @@ int alr_set_option(alr_context* ctx, const char* name, int64_t value) {
     ctx->lookahead = (int)value;
   } else if (n == "small_rir") {
     ctx->small_rir = value != 0;
+  } else if (n == "cmac_merge") {
+    ctx->cmac_merge = value != 0;
   } else if (n == "mix_group") {
     if (value < 0) return fail(ALR_ERR_INVALID, "alr_set_option: mix_group must be >= 0");
     ctx->mix_group = (int)value;
@@ -1912,8 +1923,15 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         k_mov_fused<<<std::min(ctx->fused_grid, ch.n_tasks), kCtaThreads, kFusedSmem, st>>>(fa);
         LAUNCH_CHECK(kCatFused);
       }
+      if (ctx->cmac_merge && n_cmac > 0 && n_cmacs > 0 && (long long)n_cmac + n_cmacs < 0x7fffffffLL) {
+        const int period = std::max(1, (int)(((long long)n_cmac + n_cmacs) / n_cmacs));
+        k_cmac_both<<<n_cmac + n_cmacs, kCtaThreads, kCmacSmem, st>>>(c_evs, ne, (const int*)(db + ch.off_cmac),
+                                                             (const int*)(db + ch.off_cmacs), n_cmacs, period, c_irs, c_lr,
+                                                             d_xspec, d_hspec, d_yspec);
+        LAUNCH_CHECK(kCatCmac);
+      } else {
       if (n_cmac > 0) {
-        k_cmac<<<n_cmac, kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_cmac), c_irs, c_lr, d_xspec, d_hspec,
+        k_cmac<<<n_cmac, kCtaThreads, kCmacSmem, st>>>(c_evs, ne, (const int*)(db + ch.off_cmac), c_irs, c_lr, d_xspec, d_hspec,
                                               d_yspec);
         LAUNCH_CHECK(kCatCmac);
       }
@@ -1921,6 +1939,7 @@ int alr_render(alr_context* ctx, const alr_event* events_in, int64_t n_events, c
         k_cmac_static<<<n_cmacs, kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_cmacs), c_irs, d_xspec, d_hspec,
                                                       d_yspec);
         LAUNCH_CHECK(kCatCmacStatic);
+      }
       }
       if (n_ifft > 0) {
         k_ifft_ola<<<n_ifft, kCtaThreads, 0, st>>>(c_evs, ne, (const int*)(db + ch.off_ifft), ctx->d_tw, ctx->d_zeta,

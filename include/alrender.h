@@ -208,6 +208,9 @@ int alr_set_workspace_limit(alr_context* ctx, int64_t bytes);
  *   "small_rir"   1 (default): static renders whose effective RIR fits one partition (short RIRs with at most 2 capsules, and
  *                 the dry / direct-path sub-events of compute_dry_audio) go through k_small_rir, which keeps every spectrum
  *                 in registers; 0: the general partitioned pipeline
+ *   "cmac_merge"  1: the multiply-accumulate CTAs of moving and of static events share one grid, interleaved at their ratio
+ *                 (k_cmac_both; experiment, no gain: 5.89 vs 4.27 + 1.59 ms); 0 (default): two launches, k_cmac then
+ *                 k_cmac_static
  *   "mix_group"   scenes per ambience-reduction + mixdown launch group, sized so that a group's ambience stays in L2
  *                 between the two passes; 0 = all scenes in one group */
 int alr_set_option(alr_context* ctx, const char* name, int64_t value);
