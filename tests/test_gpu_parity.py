@@ -130,7 +130,11 @@ def test_raw_moving_convolution(rnd):
 
 # ---- larger seeded cases vs the oracle's closed form --------------------------------------------------------------
 @pytest.mark.parametrize("lx,lh,c,n,sr", [(48000, 24000, 4, 21, 24000), (120000, 24000, 4, 1, 24000),
-                                          (30000, 9000, 2, 64, 24000), (96000, 48000, 8, 1, 48000)])
+                                          (30000, 9000, 2, 64, 24000), (96000, 48000, 8, 1, 48000),
+                                          # dense trajectories with long RIRs: more than 64 RIRs per run of output blocks
+                                          # (several list-building windows in k_cmac) and more than 448 (RIR, partition)
+                                          # items per window (several passes)
+                                          (40000, 40000, 2, 150, 24000), (60000, 30000, 1, 300, 24000)])
 def test_render_event_vs_oracle_large(rnd, lx, lh, c, n, sr):
     rng = np.random.default_rng(lx + n)
     audio = cases.make_audio(rng, lx)
