@@ -681,6 +681,12 @@ k_cmac(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix, 
 #define ALR_STATIC_OCC 2
 #endif
 constexpr int kStaticCh = ALR_STATIC_CH;  // capsules per thread in k_cmac_static
+// A 16-block x 2-capsule tile for long RIRs (K >= 12 partitions; fewer re-reads of the RIR spectra, which every run of output
+// blocks reads in full: 80 GB of L2 traffic per launch on the em64 shape) was SLOWER: C4 k_cmac_static 15.4 -> 19.1 ms.
+#ifndef ALR_STATIC_RUNS
+#define ALR_STATIC_RUNS 8
+#endif
+constexpr int kStaticRuns = ALR_STATIC_RUNS;  // consecutive runs of kG output blocks per k_cmac_static CTA
 __device__ __forceinline__ void cmac_static_cta(int vb, const EvDev* __restrict__ evs, int n_ev,
                                                 const int* __restrict__ prefix, const IrDev* __restrict__ irs,
                                                 const float2* __restrict__ xspec, const float2* __restrict__ hspec,
@@ -692,11 +698,9 @@ __device__ __forceinline__ void cmac_static_cta(int vb, const EvDev* __restrict_
   local /= kBinCtas;
   const int ncg = (ev.C + kStaticCh - 1) / kStaticCh;
   const int cg = local % ncg;
-  const int run = local / ncg;
+  const int run0 = (local / ncg) * kStaticRuns;
   const int c0 = cg * kStaticCh;
   const int nc = min(kStaticCh, ev.C - c0);
-  const int b0 = run * kG;
-  const int nb = min(kG, ev.B_valid - b0);
   const int bin = br * kCtaThreads + threadIdx.x;
   const int K = ev.K, C = ev.C;
   const int xnb = irs[ev.ir0].xnb;
@@ -717,6 +721,12 @@ __device__ __forceinline__ void cmac_static_cta(int vb, const EvDev* __restrict_
       for (int c = 0; c < kStaticCh; ++c) h[c] = (c < nc) ? __ldg(hbase + k * kstride + (long long)c * kCapStride) : zero;
     }
   };
+  // kStaticRuns consecutive runs per CTA: the event lookup and descriptor reads (a chain of ~10 dependent loads in front of
+  // only K = 6 steps of arithmetic at P = 4096) are paid once. 1 / 2 / 4 / 8 / 16 runs: k_cmac_static 1.59 / 1.35 / 1.24 /
+  // 1.19 / 1.18 ms per benchmark step, C2 8.01 -> 7.34 ms, C1 9.14 -> 8.36 ms (profiles/r02_micro_variants.txt).
+  for (int run = run0; run < run0 + kStaticRuns && run * kG < ev.B_valid; ++run) {
+  const int b0 = run * kG;
+  const int nb = min(kG, ev.B_valid - b0);
 #if ALR_FFMA2
   f32x2 acc[kG][kStaticCh];
 #pragma unroll
@@ -801,6 +811,7 @@ __device__ __forceinline__ void cmac_static_cta(int vb, const EvDev* __restrict_
 #else
         if (c < nc) ALR_SPEC_STORE(yspec + (ev.yslot0 + (long long)(b0 + s) * C + c0 + c) * kP + bin, acc[s][c]);
 #endif
+  }  // run
 }
 
 __global__ void __launch_bounds__(kCtaThreads, ALR_STATIC_OCC)

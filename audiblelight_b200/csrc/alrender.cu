@@ -294,7 +294,7 @@ int size_event(const alr_event& u, int idx, EvSize& z, long long ring_slots = 0,
     z.n_irfft = 0;
     z.n_cmac = 0;
   }
-  const long long n_cmac_s = (long long)ceil_div(z.B_valid, kG) * ((C + kStaticCh - 1) / kStaticCh) * kBinCtas;
+  const long long n_cmac_s = (long long)ceil_div(ceil_div(z.B_valid, kG), kStaticRuns) * ((C + kStaticCh - 1) / kStaticCh) * kBinCtas;
   z.n_cmac_static = moving ? 0 : (int)n_cmac_s;  // regular block-FIR kernel: static events (through k_cmac's item list they
                                                  // take the same time: 5.78 vs 4.26 + 1.58 ms, profiles/r02_micro_variants.txt)
   z.n_ifft = (int)n_ifft;
