@@ -63,6 +63,29 @@ def test_plan_model_random_shapes(lx, lh, n, sr):
     assert np.array_equal(ir[:, 2], np.concatenate([[0], np.cumsum(ir[:, 1])[:-1]]))
 
 
+@pytest.mark.parametrize("lx,lh,n,sr,c", [(30000, 5000, 13, 24000, 2), (60000, 30000, 300, 24000, 1),
+                                           (40000, 40000, 150, 24000, 1), (9000, 2000, 1, 24000, 2)])
+def test_cmac_item_lists_reproduce_the_block_sums(lx, lh, n, sr, c):
+    """k_cmac's item lists (one record per (RIR, partition) with a validity mask over the run's 8 outputs, built per window
+    of 64 RIRs and consumed in passes of 448) must cover exactly the (source block, partition) pairs of every output
+    block: the item-wise accumulation equals the block-wise one. The dense cases need several windows and passes."""
+    from audiblelight_b200.renderer import debug_plan
+    rng = np.random.default_rng(lx + lh + n)
+    audio = cases.make_audio(rng, lx)
+    irs = cases.make_irs(rng, c, n, lh)
+    plan = debug_plan(_job(audio, irs, sr))
+    scales = np.full(n, 512.0 if n > 1 else 1.0)
+    a = upols_model.model_convolve(audio.astype(np.float64), irs, plan, scales, n > 1, lx, cmac="blocks")
+    b = upols_model.model_convolve(audio.astype(np.float64), irs, plan, scales, n > 1, lx, cmac="items")
+    assert np.abs(a - b).max() <= 1e-12 * max(1e-30, np.abs(a).max())
+    kc = upols_model.kernel_constants()
+    runs = -(-plan["B_valid"] // kc["G"])
+    if n >= 150:  # dense trajectory: more than one window / pass per run
+        assert upols_model.model_convolve.last_lists > runs
+    else:
+        assert upols_model.model_convolve.last_lists <= runs
+
+
 def test_plan_static_full_convolution():
     from audiblelight_b200.renderer import debug_plan
     rng = np.random.default_rng(5)
