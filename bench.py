@@ -39,7 +39,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scenes-per-gpu", type=int, default=128)
+    ap.add_argument("--scenes-per-gpu", type=int, default=None,
+                    help="scenes rendered per step and GPU; default by workload: c5 / c2 128, c1 1024 (10 s scenes: fewer are "
+                         "launch-bound), c4 16 (em64 scenes: 64 channels, 2 s RIRs at 48 kHz)")
     ap.add_argument("--e2e-scenes", type=int, default=64, help="scenes per e2e step and GPU (host buffers); 16 / 32 / 64 give 27.1 / 27.8 / 28.4 K")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -47,7 +49,10 @@ def parse_args():
     ap.add_argument("--workload", default="c5", choices=["c5", "c2", "c1", "c4"])
     ap.add_argument("--cpu-workers", type=int, default=None)
     ap.add_argument("--workspace-mb", type=int, default=None, help="override the renderer's workspace limit (experiments)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.scenes_per_gpu is None:
+        args.scenes_per_gpu = {"c1": 1024, "c4": 16}.get(args.workload, 128)
+    return args
 
 
 def load_peaks():
