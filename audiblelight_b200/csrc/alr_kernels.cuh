@@ -380,17 +380,20 @@ k_x_fft(const EvDev* __restrict__ evs, int n_ev, const int* __restrict__ prefix,
 }
 
 // k_cmac: Y[b,c] = sum over IRs l, source blocks j of l and partitions k with xb0_l + j + k = b of X_l[j] * H_l[k,c].
-// One CTA per (event, run of kG consecutive output blocks, group of 4 capsules, 256 bins); a thread owns ONE bin of
-// 4 capsules for the whole run: 8 x 4 complex accumulators in registers.
-//  * The work of a CTA is a flat sequence of items (IR l, partition k). A PRODUCER iterator runs kStages-1 items
-//    ahead of the CONSUMER iterator and copies H_l[k, c0..c0+3][bin] with cp.async (LDGSTS, 8 B per thread and
-//    capsule, coalesced 256 B per warp) into a kStages-deep ring of per-thread shared-memory columns. Every thread
-//    reads back only what it copied itself, so cp.async.wait_group is the only synchronisation: no barriers, and
-//    the pipeline does not drain at IR boundaries. (Register prefetching could not cover the DRAM latency with the
-//    16 warps/SM that 64 accumulator registers allow: profiles/r01c_cmac_*.)
+// One CTA per (event, kCmacRuns consecutive runs of kGm output blocks, group of 4 capsules, 256 bins); a thread owns ONE bin
+// of 4 capsules for a whole run: 8 x 4 complex accumulators in registers.
+//  * The work of a run is a flat sequence of items (IR l, partition k), LISTED in shared memory before the pipeline starts
+//    (CmacItem: 16 bytes, one thread per RIR builds its items, warp-shuffle scan for the offsets; windows of kMaxHeads
+//    RIRs, passes of kMaxItems items for dense trajectories). The steady state of an item is one broadcast LDS.128 of its
+//    record, the H copy of the item kStages-1 ahead and the multiply-accumulates: ~87 instructions for 44 FFMAs; round 1's
+//    producer / consumer ITERATORS over per-RIR headers cost 172 (profiles/r02_micro_variants.txt).
+//  * H_l[k, c0..c0+3][256 bins] is copied with 16-byte cp.async.cg (LDGSTS.128, L1 bypassed) into a kStages-deep ring; a
+//    warp owns its 4 x 32-bin slice of every stage, so cp.async.wait_group + __syncwarp is the only synchronisation: no
+//    CTA barriers in the pipeline, and it does not drain at IR boundaries. (Register prefetching could not cover the DRAM
+//    latency with the 16 warps/SM that 64 accumulator registers allow: profiles/r01c_cmac_*.)
 //  * Each H value is used for every output block of the run it contributes to (<= 8 x 4 FFMA per 8 bytes).
-//  * The few source spectra X_l[j] an IR needs are pulled into L1 with prefetch.global.L1 by the producer (i.e.
-//    kStages-1 items early) and read through L1 with the dynamic index j = s + d0 - k.
+//  * The source spectra X_l[j] an item touches for the first time are pulled into L1 with prefetch.global.L1 when its H
+//    copy is issued (kStages-1 items early) and read through L1 at row xrow + s.
 constexpr int kG = 8;       // output blocks per CTA (k_cmac_static)
 #ifndef ALR_CMAC_G
 #define ALR_CMAC_G 8
